@@ -1,0 +1,315 @@
+// Memory-bound data-movement and small-matrix kernels around the tensor-core path:
+// layout conversion at the sgm boundary (NCHW fp32 <-> NHWC bf16), nearest-2x upsample, channel-slice
+// copies (skip concat), explicit im2row for the few convs TMA cannot gather (Cin % 64 != 0, stride 2),
+// the M<=64 "embedding" linears, sinusoidal timestep embeddings.
+#include "common.cuh"
+#include "host_util.cuh"
+#include "v3d_b200.h"
+
+namespace v3d {
+
+static inline unsigned blocks_for(long long n, int threads, int max_waves = 32) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+// ---------------- nearest 2x upsample, NHWC bf16, 16-byte vectors ----------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W,
+                                  int vpc) {
+  const long long total = static_cast<long long>(N) * (2 * H) * (2 * W) * vpc;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpc);
+    long long p = i / vpc;
+    const int ow = static_cast<int>(p % (2 * W));
+    p /= (2 * W);
+    const int oh = static_cast<int>(p % (2 * H));
+    const long long n = p / (2 * H);
+    y[i] = __ldg(&x[((n * H + (oh >> 1)) * W + (ow >> 1)) * vpc + v]);
+  }
+}
+
+// ---------------- strided 2-D copy of [rows][ncols] bf16 (16-byte vectors) ----------------
+__global__ void copy_channels_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst,
+                                     long long ldd, long long rows, int vpr) {
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vpr;
+    const int v = static_cast<int>(i % vpr);
+    *reinterpret_cast<uint4*>(dst + r * ldd + v * 8) = __ldg(reinterpret_cast<const uint4*>(src + r * lds + v * 8));
+  }
+}
+
+// ---------------- explicit im2row for 3x3 convs: y[n,oh,ow][tap*C + c], zero padded to Kpad ----------------
+__global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C,
+                                 int stride, int pad, int Ho, int Wo, int Kpad) {
+  const long long total = static_cast<long long>(N) * Ho * Wo * Kpad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kpad);
+    long long p = i / Kpad;
+    const int ow = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int oh = static_cast<int>(p % Ho);
+    const long long n = p / Ho;
+    bf16 v = __float2bfloat16(0.f);
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int ih = oh * stride + tap / 3 - pad;
+      const int iw = ow * stride + tap % 3 - pad;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((n * H + ih) * W + iw) * C + c];
+    }
+    y[i] = v;
+  }
+}
+
+// ---------------- NCHW fp32 -> NHWC bf16 (optional scale), via smem transpose ----------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int C, int HW, float scale) {
+  // grid: (ceil(HW/32), N); block 32 x 8. Each block transposes a [C][32-pixel] slab, C in chunks of 32.
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int cy = threadIdx.y; cy < 32; cy += 8) {
+      const int c = c0 + cy, p = p0 + threadIdx.x;
+      tile[cy][threadIdx.x] = (c < C && p < HW) ? x[(n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int py = threadIdx.y; py < 32; py += 8) {
+      const int p = p0 + py, c = c0 + threadIdx.x;
+      if (p < HW && c < C) y[(n * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][py] * scale);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------- NHWC (bf16 or fp32, row stride ldx, first C channels) -> NCHW fp32 ----------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int HW, long long ldx,
+                                    float scale) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int py = threadIdx.y; py < 32; py += 8) {
+      const int p = p0 + py, c = c0 + threadIdx.x;
+      tile[py][threadIdx.x] = (p < HW && c < C) ? static_cast<float>(x[(n * HW + p) * ldx + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int cy = threadIdx.y; cy < 32; cy += 8) {
+      const int c = c0 + cy, p = p0 + threadIdx.x;
+      if (c < C && p < HW) y[(n * C + c) * HW + p] = tile[threadIdx.x][cy] * scale;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------- small-M linear: y[m,n] (+)= act_out( sum_k act_in(x[m,k]) W[n,k] + b[n] ) ----------------
+// x fp32 [M,K] (M <= 64), W bf16 [N,K], y fp32 [M,N]. One warp per output column; lanes stride over K
+// with 16-byte weight loads; x is re-read through L1 (it is tiny and shared by every warp).
+constexpr int kSlMaxM = 64;
+constexpr int kSlChunk = 8;  // rows of x processed per pass over the weight row
+
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W, const float* __restrict__ bias,
+                    float* __restrict__ y, int M, int K, int N, int act_in, int act_out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const bf16* wr = W + static_cast<long long>(n) * K;
+  const float bv = bias ? bias[n] : 0.f;
+  for (int m0 = 0; m0 < M; m0 += kSlChunk) {
+    float acc[kSlChunk];
+#pragma unroll
+    for (int i = 0; i < kSlChunk; ++i) acc[i] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(wv[j]);
+        w[2 * j] = f.x;
+        w[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int i = 0; i < kSlChunk; ++i) {
+        if (m0 + i < M) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * K + k));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * K + k + 4));
+          float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (act_in == V3D_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = xv[j] / (1.0f + expf(-xv[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xv[j], w[j], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSlChunk; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (lane == 0 && m0 + i < M) {
+        float v = s + bv;
+        if (act_out == V3D_ACT_SILU) v = v / (1.0f + expf(-v));
+        float* o = y + static_cast<long long>(m0 + i) * N + n;
+        *o = accumulate ? *o + v : v;
+      }
+    }
+  }
+}
+
+// ---------------- sinusoidal embedding: out[i] = [cos(t_i f_k) | sin(t_i f_k)], f_k = exp(-ln(P) k / half) ----
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim,
+                                          float max_period) {
+  const int half = dim / 2;
+  const int total = n * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / dim, c = i - r * dim;
+    float v = 0.f;
+    if (c < 2 * half) {
+      const int k = c < half ? c : c - half;
+      const float f = expf(-logf(max_period) * static_cast<float>(k) / static_cast<float>(half));
+      const float a = t[r] * f;
+      v = c < half ? cosf(a) : sinf(a);
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                                long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    o[i] = a[i] + b[i];
+}
+
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" {
+
+/* F.interpolate(scale_factor=2, mode="nearest") on NHWC bf16 (openaimodel.py:164; model.py:68). */
+int v3d_upsample_nearest2x(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!x || !y || C % 8 != 0 || N <= 0 || H <= 0 || W <= 0) {
+    set_error("v3d_upsample_nearest2x: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  const long long total = 4LL * N * H * W * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8);
+  V3D_CHECK_LAUNCH("upsample2x_kernel");
+  return V3D_OK;
+}
+
+/* Copy a [rows][ncols] bf16 block between row-strided buffers: the two halves of
+ * th.cat([h, hs.pop()], dim=1) (video_model.py:483) written into one NHWC buffer. */
+int v3d_copy_channels(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int32_t ncols,
+                      void* stream) {
+  if (!src || !dst || ncols % 8 != 0 || ld_src % 8 != 0 || ld_dst % 8 != 0 || rows <= 0) {
+    set_error("v3d_copy_channels: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  copy_channels_kernel<<<blocks_for(rows * (ncols / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(src), ld_src, static_cast<bf16*>(dst), ld_dst, rows, ncols / 8);
+  V3D_CHECK_LAUNCH("copy_channels_kernel");
+  return V3D_OK;
+}
+
+/* Explicit im2row (tap-major, then channel; zero-padded to Kpad columns) for 3x3 convs the TMA gather
+ * does not cover: Cin % 64 != 0 (video_model.py:189 8->320; model.py:651 4->512) and stride 2
+ * (openaimodel.py:202-209 Downsample; model.py:82-90 with pad=0). */
+int v3d_im2col3x3(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, int32_t pad,
+                  int32_t Hout, int32_t Wout, int32_t Kpad, void* stream) {
+  if (!x || !y || Kpad < 9 * C || stride <= 0) {
+    set_error("v3d_im2col3x3: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  const long long total = static_cast<long long>(N) * Hout * Wout * Kpad;
+  im2col3x3_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C, stride, pad, Hout, Wout, Kpad);
+  V3D_CHECK_LAUNCH("im2col3x3_kernel");
+  return V3D_OK;
+}
+
+/* sgm boundary: the reference hands the network NCHW fp32 (wrappers.py:27, video_diffusion.py:184). */
+int v3d_nchw_f32_to_nhwc_bf16(const void* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W, float scale,
+                              void* stream) {
+  if (!x || !y || N <= 0 || C <= 0 || N > 65535) {
+    set_error("v3d_nchw_f32_to_nhwc_bf16: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  dim3 grid((H * W + 31) / 32, N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<bf16*>(y), C, H * W, scale);
+  V3D_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return V3D_OK;
+}
+
+int v3d_nhwc_to_nchw_f32(const void* x, void* y, int32_t N, int32_t C, int32_t HW, int64_t ldx, int32_t src_fp32,
+                         float scale, void* stream) {
+  if (!x || !y || N <= 0 || C <= 0 || N > 65535) {
+    set_error("v3d_nhwc_to_nchw_f32: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  dim3 grid((HW + 31) / 32, N), block(32, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_fp32)
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), C, HW,
+                                                       ldx, scale);
+  else
+    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), static_cast<float*>(y), C, HW,
+                                                      ldx, scale);
+  V3D_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+  return V3D_OK;
+}
+
+/* The M<=64 linears on embeddings: time_embed / label_emb (video_model.py:151-182,456-461), ResBlock
+ * emb_layers (openaimodel.py:291-297), time_pos_embed (video_attention.py:220-224,275), and the
+ * single-token cross-attention collapse to_out(to_v(ctx)) (attention.py:277-283 with one key). */
+int v3d_small_linear(const void* x, const void* W, const void* bias, void* y, int32_t M, int32_t K, int32_t N,
+                     int32_t act_in, int32_t act_out, int32_t accumulate, void* stream) {
+  if (!x || !W || !y || M <= 0 || M > kSlMaxM || K % 8 != 0 || N <= 0) {
+    set_error("v3d_small_linear: bad args M=%d K=%d N=%d", M, K, N);
+    return V3D_ERR_BAD_ARG;
+  }
+  const int warps = 8;
+  small_linear_kernel<<<(N + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<const bf16*>(W), static_cast<const float*>(bias),
+      static_cast<float*>(y), M, K, N, act_in, act_out, accumulate);
+  V3D_CHECK_LAUNCH("small_linear_kernel");
+  return V3D_OK;
+}
+
+/* timestep_embedding (diffusionmodules/util.py:207-231): cos | sin halves, fp32. */
+int v3d_timestep_embedding(const void* t, void* out, int32_t n, int32_t dim, float max_period, void* stream) {
+  if (!t || !out || n <= 0 || dim <= 0) {
+    set_error("v3d_timestep_embedding: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  timestep_embedding_kernel<<<blocks_for(static_cast<long long>(n) * dim, 256), 256, 0,
+                              static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(t),
+                                                                   static_cast<float*>(out), n, dim, max_period);
+  V3D_CHECK_LAUNCH("timestep_embedding_kernel");
+  return V3D_OK;
+}
+
+int v3d_add_rows(const void* a, const void* b, void* out, int32_t rows, int32_t cols, void* stream) {
+  if (!a || !b || !out) {
+    set_error("v3d_add_rows: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  const long long n = static_cast<long long>(rows) * cols;
+  add_rows_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(out), n);
+  V3D_CHECK_LAUNCH("add_rows_kernel");
+  return V3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,493 @@
+// tcgen05 GEMM / temporal-conv / implicit-GEMM 3x3 conv for sm_100a.
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      : TMA producer  (A tile 128x64 bf16 + B tile BNx64 bf16 per pipeline stage, 128B swizzle)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> bias / per-frame bias / SiLU / GEGLU / residual blend ->
+//                 bf16 or fp32 stores). Two TMEM accumulator stages so the epilogue of tile i overlaps
+//                 the main loop of tile i+1.
+// Operand gather modes (see include/v3d_b200.h): linear rows, 3-tap temporal shift, 3x3 spatial taps.
+// The im2row never exists in memory: each (tap, 64-channel) K-block is one TMA box whose out-of-bounds
+// part is zero-filled by the hardware, which is exactly the conv zero padding.
+#include "common.cuh"
+#include "host_util.cuh"
+#include "v3d_b200.h"
+
+namespace v3d {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 225 * 1024;
+
+struct GemmEpi {
+  void* D;
+  const float* bias;
+  const float* fbias;
+  const bf16* R1;
+  const bf16* R2;
+  long long ldd, ldr1, ldr2;
+  int batch, rows_per_batch, tiles_per_batch;
+  int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
+  int rows_per_frame, act, out_fp32;
+  int b_batched;
+  // conv3x3 geometry
+  int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles;
+  float s0, s1, s2;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
+  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const GemmEpi p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::NSTAGE;
+  uint64_t* tfull_bar = empty_bar + C::NSTAGE;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < C::NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = p.ntaps * p.kpt;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        int c1, c2, c3 = 0;
+        if (CONV) {
+          const int tw = m_tile % p.tiles_w;
+          const int th = (m_tile / p.tiles_w) % p.tiles_h;
+          const int tn = m_tile / (p.tiles_w * p.tiles_h);
+          c1 = tw * p.bw;
+          c2 = th * p.bh;
+          c3 = tn * p.bn;
+        } else {
+          c2 = m_tile / p.tiles_per_batch;
+          c1 = (m_tile % p.tiles_per_batch) * BM;
+        }
+        const int bz = p.b_batched ? c2 : 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int tap = kb / p.kpt;
+          const int kc = (kb - tap * p.kpt) * BK;
+          if (CONV) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
+          } else {
+            tma_load_3d(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift,
+                        c2);
+          }
+          tma_load_3d(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN, bz);
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128B swizzle atom (encoded >>4)
+            tc_mma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                       idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const bool geglu = p.act == V3D_ACT_GEGLU;
+    const int out_cols = geglu ? BN / 2 : BN;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      long long row;
+      bool valid;
+      if (CONV) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w = r % p.bw;
+        const int h = (r / p.bw) % p.bh;
+        const int n = r / (p.bw * p.bh);
+        const int img = tn * p.bn + n;
+        valid = img < p.cn;
+        row = (static_cast<long long>(img) * p.ch + (th * p.bh + h)) * p.cw + (tw * p.bw + w);
+      } else {
+        const int b = m_tile / p.tiles_per_batch;
+        const int m = (m_tile % p.tiles_per_batch) * BM + r;
+        valid = m < p.rows_per_batch;
+        row = static_cast<long long>(b) * p.rows_per_batch + m;
+      }
+      const float* fb = nullptr;
+      if (p.fbias != nullptr && valid)
+        fb = p.fbias + (row / p.rows_per_frame) * static_cast<long long>(p.N);
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc =
+          tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int c = 0; c < out_cols; c += 16) {
+        uint32_t v[16];
+        uint32_t g[16];
+        tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
+        if (geglu) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+          const int ncol = n_tile * BN + c;  // column in the (packed) N space
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + ncol + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (fb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(fb + ncol + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (geglu) {
+            float gt[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + ncol + BN / 2 + j);
+                gt[j] += b4.x; gt[j + 1] += b4.y; gt[j + 2] += b4.z; gt[j + 3] += b4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_f(gt[j]);
+          } else if (p.act == V3D_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+          }
+          const int ocol = n_tile * out_cols + c;  // column in the output
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
+          if (p.R1 != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.R1 + row * p.ldr1 + ocol);
+            const uint4 a = rp[0], b = rp[1];
+            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 t = unpack_bf16x2(u[j]);
+              f[2 * j] += p.s1 * t.x;
+              f[2 * j + 1] += p.s1 * t.y;
+            }
+          }
+          if (p.R2 != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.R2 + row * p.ldr2 + ocol);
+            const uint4 a = rp[0], b = rp[1];
+            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 t = unpack_bf16x2(u[j]);
+              f[2 * j] += p.s2 * t.x;
+              f[2 * j + 1] += p.s2 * t.y;
+            }
+          }
+          if (p.out_fp32) {
+            float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + ocol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* dp = reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + row * p.ldd + ocol);
+            dp[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            dp[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                               pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int pick_block_n(int N, int act) {
+  static const int cands[] = {256, 160, 128, 64, 32, 16};
+  for (int c : cands) {
+    if (N % c != 0) continue;
+    if (act == V3D_ACT_GEGLU && (c / 2) % 16 != 0) continue;
+    return c;
+  }
+  return 0;
+}
+
+template <int BN, bool CONV>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, CONV>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return V3D_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int total = epi.num_m_tiles * epi.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, epi);
+  V3D_CHECK_LAUNCH("gemm_tc_kernel");
+  return V3D_OK;
+}
+
+template <bool CONV>
+static int dispatch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
+                       cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch<256, CONV>(ma, mb, epi, st);
+    case 160: return launch<160, CONV>(ma, mb, epi, st);
+    case 128: return launch<128, CONV>(ma, mb, epi, st);
+    case 64: return launch<64, CONV>(ma, mb, epi, st);
+    case 32: return launch<32, CONV>(ma, mb, epi, st);
+    case 16: return launch<16, CONV>(ma, mb, epi, st);
+    default: set_error("unsupported block_n %d", bn); return V3D_ERR_BAD_ARG;
+  }
+}
+
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" int v3d_gemm_pick_block_n(int32_t N, int32_t act) { return pick_block_n(N, act); }
+
+extern "C" int v3d_geglu_pack_rows(int32_t n_out, int32_t block_n, int32_t* perm) {
+  if (n_out <= 0 || block_n <= 0 || (block_n & 1) || (2 * n_out) % block_n != 0 || perm == nullptr) {
+    set_error("v3d_geglu_pack_rows: bad n_out=%d block_n=%d", n_out, block_n);
+    return V3D_ERR_BAD_ARG;
+  }
+  const int half = block_n / 2;
+  const int tiles = 2 * n_out / block_n;
+  for (int t = 0; t < tiles; ++t) {
+    for (int j = 0; j < half; ++j) {
+      perm[t * block_n + j] = t * half + j;                 // value rows
+      perm[t * block_n + half + j] = n_out + t * half + j;  // gate rows
+    }
+  }
+  return V3D_OK;
+}
+
+extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
+  if (a == nullptr || a->A == nullptr || a->B == nullptr || a->D == nullptr) {
+    set_error("v3d_gemm_bf16: null pointer");
+    return V3D_ERR_BAD_ARG;
+  }
+  const bool conv = a->conv_w > 0;
+  const int ntaps = conv ? 9 : (a->ntaps > 0 ? a->ntaps : 1);
+  if (a->K <= 0 || a->K % BK != 0 || a->N <= 0 || a->N % 16 != 0) {
+    set_error("v3d_gemm_bf16: K=%d must be a multiple of 64 and N=%d of 16", a->K, a->N);
+    return V3D_ERR_BAD_ARG;
+  }
+  if (!conv && ntaps != 1 && ntaps != 3) {
+    set_error("v3d_gemm_bf16: ntaps must be 1 or 3");
+    return V3D_ERR_BAD_ARG;
+  }
+  if ((a->lda % 8) || (a->ldb % 8) || (a->ldd % 8) || (a->R1 && a->ldr1 % 8) || (a->R2 && a->ldr2 % 8)) {
+    set_error("v3d_gemm_bf16: leading dimensions must be multiples of 8 elements");
+    return V3D_ERR_BAD_ARG;
+  }
+  const int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, a->act);
+  if (bn == 0 || a->N % bn != 0 || (a->act == V3D_ACT_GEGLU && (bn / 2) % 16 != 0)) {
+    set_error("v3d_gemm_bf16: no valid N tile for N=%d act=%d block_n=%d", a->N, a->act, a->block_n);
+    return V3D_ERR_BAD_ARG;
+  }
+
+  GemmEpi e;
+  memset(&e, 0, sizeof(e));
+  e.D = a->D;
+  e.bias = a->bias;
+  e.fbias = a->fbias;
+  e.R1 = static_cast<const bf16*>(a->R1);
+  e.R2 = static_cast<const bf16*>(a->R2);
+  e.ldd = a->ldd;
+  e.ldr1 = a->ldr1;
+  e.ldr2 = a->ldr2;
+  e.N = a->N;
+  e.kpt = a->K / BK;
+  e.ntaps = ntaps;
+  e.tap_shift = a->tap_shift;
+  e.rows_per_frame = a->rows_per_frame > 0 ? a->rows_per_frame : 1;
+  e.act = a->act;
+  e.out_fp32 = a->out_fp32;
+  e.s0 = a->s0;
+  e.s1 = a->s1;
+  e.s2 = a->s2;
+  e.num_n_tiles = a->N / bn;
+
+  CUtensorMap ma, mb;
+  int rc;
+  int b_batch = 1;
+  if (conv) {
+    const int W = a->conv_w, H = a->conv_h, NI = a->conv_n;
+    if (H <= 0 || NI <= 0) {
+      set_error("v3d_gemm_bf16: bad conv geometry");
+      return V3D_ERR_BAD_ARG;
+    }
+    const int bw = W < BM ? W : BM;
+    if (BM % bw != 0 || W % bw != 0) {
+      set_error("conv3x3: width %d does not tile into 128-pixel boxes", W);
+      return V3D_ERR_UNSUPPORTED;
+    }
+    int bh = BM / bw;
+    if (bh > H) bh = H;
+    if (H % bh != 0 || (BM / bw) % bh != 0) {
+      set_error("conv3x3: height %d does not tile into 128-pixel boxes (bw=%d)", H, bw);
+      return V3D_ERR_UNSUPPORTED;
+    }
+    const int bnimg = BM / (bw * bh);
+    e.cn = NI; e.ch = H; e.cw = W; e.bw = bw; e.bh = bh; e.bn = bnimg;
+    e.tiles_w = W / bw;
+    e.tiles_h = H / bh;
+    e.num_m_tiles = e.tiles_w * e.tiles_h * ((NI + bnimg - 1) / bnimg);
+    e.batch = 1; e.rows_per_batch = NI * H * W; e.tiles_per_batch = 1;
+    const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+    const uint64_t str[3] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * W, (uint64_t)a->lda * 2 * W * H};
+    const uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+    rc = make_tmap_bf16(&ma, a->A, 4, dims, str, box);
+    if (rc) return rc;
+  } else {
+    if (a->batch <= 0 || a->rows_per_batch <= 0) {
+      set_error("v3d_gemm_bf16: bad batch/rows");
+      return V3D_ERR_BAD_ARG;
+    }
+    e.batch = a->batch;
+    e.rows_per_batch = a->rows_per_batch;
+    e.tiles_per_batch = (a->rows_per_batch + BM - 1) / BM;
+    e.num_m_tiles = e.batch * e.tiles_per_batch;
+    const uint64_t abs_ = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->rows_per_batch * a->lda;
+    if (abs_ % 8 != 0) {
+      set_error("v3d_gemm_bf16: a_batch_stride must be a multiple of 8");
+      return V3D_ERR_BAD_ARG;
+    }
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->lda * 2, abs_ * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    rc = make_tmap_bf16(&ma, a->A, 3, dims, str, box);
+    if (rc) return rc;
+    if (a->b_batch_stride != 0) {
+      b_batch = a->batch;
+      e.b_batched = 1;
+    }
+  }
+  {
+    const uint64_t ktot = (uint64_t)ntaps * a->K;
+    const uint64_t bbs = b_batch > 1 ? (uint64_t)a->b_batch_stride : (uint64_t)a->N * a->ldb;
+    const uint64_t dims[3] = {ktot, (uint64_t)a->N, (uint64_t)b_batch};
+    const uint64_t str[2] = {(uint64_t)a->ldb * 2, bbs * 2};
+    const uint32_t box[3] = {BK, (uint32_t)bn, 1};
+    rc = make_tmap_bf16(&mb, a->B, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return conv ? dispatch_bn<true>(bn, ma, mb, e, st) : dispatch_bn<false>(bn, ma, mb, e, st);
+}

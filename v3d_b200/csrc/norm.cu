@@ -1,0 +1,365 @@
+// Memory-bound normalisation kernels on NHWC / token-major bf16 activations (fp32 statistics):
+// GroupNorm(32) statistics + apply(+SiLU), LayerNorm (+ fused per-frame add), row softmax.
+// All global accesses are 16-byte vectors along the contiguous channel dimension.
+#include "common.cuh"
+#include "host_util.cuh"
+#include "v3d_b200.h"
+
+namespace v3d {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[sample][group] = {sum, sumsq} (double), accumulated with atomics.
+// grid = (row chunks, samples); each thread owns one 8-channel vector column and strides over rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, long long rows_per_sample,
+                int C, long long ldx, int groups, int rows_per_cta) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int vpr = C >> 3;           // 16-byte vectors per row
+  const int sample = blockIdx.y;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long row1 = row0 + rows_per_cta;
+  if (row1 > rows_per_sample) row1 = rows_per_sample;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+
+  const int lanes_r = blockDim.x / vpr;  // row lanes (>=1 guaranteed by host)
+  const int vc = threadIdx.x % vpr;
+  const int rl = threadIdx.x / vpr;
+  if (rl < lanes_r) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const bf16* base = x + (static_cast<long long>(sample) * rows_per_sample) * ldx + vc * 8;
+    for (long long r = row0 + rl; r < row1; r += lanes_r) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * ldx));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[vc * 8 + j], s[j]);
+      atomicAdd(&s_acc[C + vc * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int c = 0; c < cg; ++c) {
+      ds += static_cast<double>(s_acc[g * cg + c]);
+      dq += static_cast<double>(s_acc[C + g * cg + c]);
+    }
+    double* o = stats + (static_cast<long long>(sample) * groups + g) * 2;
+    atomicAdd(o, ds);
+    atomicAdd(o + 1, dq);
+  }
+}
+
+// y = act((x - mean) * rstd * gamma + beta); per-sample per-channel scale/shift precomputed in smem.
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const double* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                long long rows_per_sample, int C, long long ldx, int groups, float eps, int silu,
+                int rows_per_cta) {
+  extern __shared__ float s_ab[];  // [2][C]: scale, shift
+  const int sample = blockIdx.y;
+  const int cg = C / groups;
+  const double cnt = static_cast<double>(rows_per_sample) * cg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const double* st = stats + (static_cast<long long>(sample) * groups + g) * 2;
+    const double mean = st[0] / cnt;
+    double var = st[1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float a = rstd * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - static_cast<float>(mean) * a;
+  }
+  __syncthreads();
+  const int vpr = C >> 3;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long row1 = row0 + rows_per_cta;
+  if (row1 > rows_per_sample) row1 = rows_per_sample;
+  const long long nvec = (row1 - row0) * vpr;
+  const long long srow = static_cast<long long>(sample) * rows_per_sample;
+  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const long long r = row0 + i / vpr;
+    const int vc = static_cast<int>(i % vpr);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (srow + r) * ldx + vc * 8));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      const int c = vc * 8 + 2 * j;
+      float a = f.x * s_ab[c] + s_ab[C + c];
+      float b = f.y * s_ab[c + 1] + s_ab[C + c + 1];
+      if (silu) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    *reinterpret_cast<uint4*>(y + (srow + r) * static_cast<long long>(C) + vc * 8) =
+        make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C (<= 2048), one warp per row, row held in registers.
+//   z = x[row] + add[row / rows_per_frame]   (add optional, fp32)
+//   ysum[row] = bf16(z)                      (optional)
+//   y[row] = (z - mean) * rstd * gamma + beta
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 8;  // 8 vectors * 8 elements * 32 lanes = 2048 channels
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16* __restrict__ ysum,
+                 bf16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 long long rows, int C, int rows_per_frame, float eps) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int vpr = C >> 3;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * warps) {
+    float v[kLnMaxVec][8];
+    const bf16* xr = x + row * C;
+    const float* ar = add ? add + (row / rows_per_frame) * C : nullptr;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int vc = lane + i * 32;
+      if (vc < vpr) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vc * 8));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          v[i][2 * j] = f.x;
+          v[i][2 * j + 1] = f.y;
+        }
+        if (ar) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ar + vc * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(ar + vc * 8 + 4));
+          v[i][0] += a0.x; v[i][1] += a0.y; v[i][2] += a0.z; v[i][3] += a0.w;
+          v[i][4] += a1.x; v[i][5] += a1.y; v[i][6] += a1.z; v[i][7] += a1.w;
+          if (ysum) {
+            // round once so that the residual stream and the LN input agree bit-for-bit
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16_rn(v[i][j]));
+            *reinterpret_cast<uint4*>(ysum + row * C + vc * 8) =
+                make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]),
+                           pack_bf16x2(v[i][4], v[i][5]), pack_bf16x2(v[i][6], v[i][7]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (lane + i * 32 < vpr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          q += d * d;
+        }
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int vc = lane + i * 32;
+      if (vc < vpr) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vc * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vc * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vc * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vc * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+        *reinterpret_cast<uint4*>(y + row * C + vc * 8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                       pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-place row softmax over bf16 scores (decoder AttnBlock, one 4096-wide row per CTA).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(bf16* __restrict__ x, int n, float scale) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  bf16* row = x + static_cast<long long>(blockIdx.x) * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = n >> 3;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      m = fmaxf(m, fmaxf(f.x, f.y));
+    }
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) t = fmaxf(t, red[i]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast * scale;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s += __expf(f.x * scale - m) + __expf(f.y * scale - m);
+    }
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    bcast = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      o[j] = pack_bf16x2(__expf(f.x * scale - m) * inv, __expf(f.y * scale - m) * inv);
+    }
+    *reinterpret_cast<uint4*>(row + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static int pick_rows_per_cta(long long rows_per_sample, int nsamples) {
+  // aim for >= ~4 waves of CTAs over the SMs while keeping at least 32 rows per CTA
+  const long long target = 4LL * num_sms();
+  long long chunks = (target + nsamples - 1) / nsamples;
+  if (chunks < 1) chunks = 1;
+  long long rpc = (rows_per_sample + chunks - 1) / chunks;
+  if (rpc < 32) rpc = 32;
+  if (rpc > rows_per_sample) rpc = rows_per_sample;
+  return static_cast<int>(rpc);
+}
+
+}  // namespace v3d
+
+using namespace v3d;
+
+extern "C" {
+
+/* GroupNorm statistics over [nsamples][rows_per_sample][C] (bf16, row stride ldx) -> stats double
+ * [nsamples][groups][2] = {sum, sumsq}. rows_per_sample = H*W for 2-D GroupNorm32/Normalize
+ * (diffusionmodules/util.py:259-276, attention.py:130-133, model.py:52-55) and T*H*W for the 3-D
+ * time_stack ResBlock (openaimodel.py:267-271 with dims=3: reduction over (C/32, T, H, W)). */
+int v3d_groupnorm_stats(const void* x, void* stats, int64_t rows_per_sample, int32_t nsamples, int32_t C,
+                        int32_t ldx, int32_t groups, void* stream) {
+  if (!x || !stats || C % 8 != 0 || C % groups != 0 || C / 8 > 512 || ldx % 8 != 0 ||
+      rows_per_sample <= 0 || nsamples <= 0) {
+    set_error("v3d_groupnorm_stats: bad args C=%d groups=%d ldx=%d", C, groups, ldx);
+    return V3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * nsamples, st);
+  if (e != cudaSuccess) {
+    set_error("memset stats: %s", cudaGetErrorString(e));
+    return V3D_ERR_CUDA;
+  }
+  const int rpc = pick_rows_per_cta(rows_per_sample, nsamples);
+  dim3 grid(static_cast<unsigned>((rows_per_sample + rpc - 1) / rpc), nsamples);
+  const int vpr = C / 8;
+  const int lanes_r = kGnThreads / vpr > 0 ? kGnThreads / vpr : 1;
+  gn_stats_kernel<<<grid, vpr * lanes_r, 2 * C * sizeof(float), st>>>(
+      static_cast<const bf16*>(x), static_cast<double*>(stats), rows_per_sample, C, ldx, groups, rpc);
+  V3D_CHECK_LAUNCH("gn_stats_kernel");
+  return V3D_OK;
+}
+
+/* y[dense, ld=C] = act(GroupNorm(x; stats, gamma, beta, eps)), act = SiLU when silu != 0
+ * (fuses normalization() + nn.SiLU of openaimodel.py:267-271,300-303; model.py:131-143 nonlinearity). */
+int v3d_groupnorm_apply(const void* x, void* y, const void* stats, const void* gamma, const void* beta,
+                        int64_t rows_per_sample, int32_t nsamples, int32_t C, int32_t ldx, int32_t groups,
+                        float eps, int32_t silu, void* stream) {
+  if (!x || !y || !stats || !gamma || !beta || C % 8 != 0 || C % groups != 0 || ldx % 8 != 0) {
+    set_error("v3d_groupnorm_apply: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rpc = pick_rows_per_cta(rows_per_sample, nsamples);
+  dim3 grid(static_cast<unsigned>((rows_per_sample + rpc - 1) / rpc), nsamples);
+  gn_apply_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), st>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), static_cast<const double*>(stats),
+      static_cast<const float*>(gamma), static_cast<const float*>(beta), rows_per_sample, C, ldx, groups,
+      eps, silu, rpc);
+  V3D_CHECK_LAUNCH("gn_apply_kernel");
+  return V3D_OK;
+}
+
+/* LayerNorm (attention.py:525-527, video_attention.py:51,79,93-94) with the optional fused
+ * "x_mix = x + emb" of video_attention.py:286-287 (add = per-frame fp32 vectors, ysum receives x+emb). */
+int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const void* gamma, const void* beta,
+                  int64_t rows, int32_t C, int32_t rows_per_frame, float eps, void* stream) {
+  if (!x || !y || !gamma || !beta || C % 8 != 0 || C > kLnMaxVec * 256 || rows <= 0) {
+    set_error("v3d_layernorm: bad args C=%d", C);
+    return V3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  long long blocks = (rows + warps - 1) / warps;
+  const long long cap = 16LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
+      static_cast<const bf16*>(x), static_cast<const float*>(add), static_cast<bf16*>(ysum),
+      static_cast<bf16*>(y), static_cast<const float*>(gamma), static_cast<const float*>(beta), rows, C,
+      rows_per_frame > 0 ? rows_per_frame : 1, eps);
+  V3D_CHECK_LAUNCH("layernorm_kernel");
+  return V3D_OK;
+}
+
+/* In-place softmax(scale * x) over rows of n bf16 scores (decoder AttnBlock, model.py:190-192). */
+int v3d_softmax_rows(void* x, int64_t rows, int32_t n, float scale, void* stream) {
+  if (!x || n % 8 != 0 || rows <= 0 || rows > 0x7fffffffLL) {
+    set_error("v3d_softmax_rows: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(x), n, scale);
+  V3D_CHECK_LAUNCH("softmax_rows_kernel");
+  return V3D_OK;
+}
+
+}  // extern "C"
