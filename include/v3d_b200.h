@@ -67,6 +67,7 @@ typedef struct v3d_gemm_args {
   const void* R1;     /* bf16 [rows][ldr1] or NULL */
   const void* R2;     /* bf16 [rows][ldr2] or NULL */
   int64_t lda, ldb, ldd, ldr1, ldr2;
+  int64_t ldfb; /* row stride of fbias in floats; 0 -> N */
   int64_t a_batch_stride, b_batch_stride; /* elements; b_batch_stride == 0 -> B shared by all batch items */
   int32_t batch, rows_per_batch;
   int32_t N, K;

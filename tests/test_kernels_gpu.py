@@ -283,7 +283,8 @@ def test_upsample_copy_im2col():
         unf = F.unfold(xp, 3, padding=pad, stride=stride)  # [n, cc*9, L] with (c, ky, kx) ordering
         unf = unf.reshape(n, cc, 9, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, 9 * cc)
         assert torch.equal(col[:, :9 * cc].float(), unf), (cc, stride, pad)
-        assert col[:, 9 * cc:].abs().max() == 0
+        if kpad > 9 * cc:
+            assert col[:, 9 * cc:].abs().max() == 0
 
 
 def test_layout_conversions():

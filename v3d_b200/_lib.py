@@ -23,6 +23,7 @@ class GemmArgs(C.Structure):
         ("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p),
         ("bias", C.c_void_p), ("fbias", C.c_void_p), ("R1", C.c_void_p), ("R2", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64), ("ldr1", C.c_int64), ("ldr2", C.c_int64),
+        ("ldfb", C.c_int64),
         ("a_batch_stride", C.c_int64), ("b_batch_stride", C.c_int64),
         ("batch", C.c_int32), ("rows_per_batch", C.c_int32),
         ("N", C.c_int32), ("K", C.c_int32),

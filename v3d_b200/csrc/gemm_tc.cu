@@ -26,7 +26,7 @@ struct GemmEpi {
   const float* fbias;
   const bf16* R1;
   const bf16* R2;
-  long long ldd, ldr1, ldr2;
+  long long ldd, ldr1, ldr2, ldfb;
   int batch, rows_per_batch, tiles_per_batch;
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
   int rows_per_frame, act, out_fp32;
@@ -202,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       const float* fb = nullptr;
       if (p.fbias != nullptr && valid)
-        fb = p.fbias + (row / p.rows_per_frame) * static_cast<long long>(p.N);
+        fb = p.fbias + (row / p.rows_per_frame) * p.ldfb;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -392,7 +392,8 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     set_error("v3d_gemm_bf16: ntaps must be 1 or 3");
     return V3D_ERR_BAD_ARG;
   }
-  if ((a->lda % 8) || (a->ldb % 8) || (a->ldd % 8) || (a->R1 && a->ldr1 % 8) || (a->R2 && a->ldr2 % 8)) {
+  if ((a->lda % 8) || (a->ldb % 8) || (a->ldd % 8) || (a->R1 && a->ldr1 % 8) || (a->R2 && a->ldr2 % 8) ||
+      (a->ldfb % 4)) {
     set_error("v3d_gemm_bf16: leading dimensions must be multiples of 8 elements");
     return V3D_ERR_BAD_ARG;
   }
@@ -412,6 +413,7 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   e.ldd = a->ldd;
   e.ldr1 = a->ldr1;
   e.ldr2 = a->ldr2;
+  e.ldfb = a->ldfb > 0 ? a->ldfb : a->N;
   e.N = a->N;
   e.kpt = a->K / BK;
   e.ntaps = ntaps;

@@ -51,6 +51,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
          rows_per_batch: int, batch: int = 1, lda: Optional[int] = None, ldb: Optional[int] = None,
          ldd: Optional[int] = None, a_batch_stride: int = 0, b_batch_stride: int = 0,
          bias: Optional[torch.Tensor] = None, fbias: Optional[torch.Tensor] = None, rows_per_frame: int = 1,
+         ldfb: int = 0,
          r1: Optional[torch.Tensor] = None, ldr1: int = 0, r2: Optional[torch.Tensor] = None, ldr2: int = 0,
          s0: float = 1.0, s1: float = 1.0, s2: float = 1.0, act: int = ACT_NONE, ntaps: int = 1,
          tap_shift: int = 0, conv: Optional[tuple] = None, block_n: int = 0) -> torch.Tensor:
@@ -77,6 +78,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
     g.N, g.K = N, K
     g.ntaps, g.tap_shift = ntaps, tap_shift
     g.rows_per_frame = rows_per_frame
+    g.ldfb = ldfb
     g.act = act
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     if conv is not None:
