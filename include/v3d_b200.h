@@ -110,6 +110,8 @@ int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const voi
                   int64_t rows, int32_t C, int32_t rows_per_frame, float eps, void* stream);
 /* in-place softmax(scale * x) over rows of n bf16 scores (decoder AttnBlock, model.py:190-192). */
 int v3d_softmax_rows(void* x, int64_t rows, int32_t n, float scale, void* stream);
+/* same, fp32 scores in, bf16 probabilities out (separate buffers). */
+int v3d_softmax_rows_f32(const void* x, void* y, int64_t rows, int32_t n, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention (attention.cu), head dim 64. q/k/v are column slices of one packed projection output
@@ -141,14 +143,19 @@ int v3d_nchw_f32_to_nhwc_bf16(const void* x, void* y, int32_t N, int32_t C, int3
                               void* stream);
 int v3d_nhwc_to_nchw_f32(const void* x, void* y, int32_t N, int32_t C, int32_t HW, int64_t ldx, int32_t src_fp32,
                          float scale, void* stream);
-/* y[M,N] fp32 (+)= act_out(act_in(x[M,K] fp32) W[N,K]^T (bf16) + bias), M <= 64: time_embed/label_emb
+/* y[M,N] fp32 (+)= act_out(act_in(x[M,K] fp32) W[N,K]^T (bf16) + bias), M <= 64, row strides ldx/ldy
+ * in floats (0 -> dense): time_embed/label_emb
  * (video_model.py:151-182,456-461), emb_layers (openaimodel.py:291-297), time_pos_embed
  * (video_attention.py:220-224,275), single-token cross-attention to_out(to_v(ctx)) (attention.py:277-283). */
 int v3d_small_linear(const void* x, const void* W, const void* bias, void* y, int32_t M, int32_t K, int32_t N,
-                     int32_t act_in, int32_t act_out, int32_t accumulate, void* stream);
+                     int32_t act_in, int32_t act_out, int32_t accumulate, int64_t ldx, int64_t ldy, void* stream);
 /* timestep_embedding (diffusionmodules/util.py:207-231): out[n][dim] = cos | sin, fp32. */
 int v3d_timestep_embedding(const void* t, void* out, int32_t n, int32_t dim, float max_period, void* stream);
 int v3d_add_rows(const void* a, const void* b, void* out, int32_t rows, int32_t cols, void* stream);
+/* AE3DConv.time_mix_conv (temporal_ae.py:94-107): Conv3d(C,C,(3,1,1)) over frames, C <= 4; x NHWC fp32 (row
+ * stride ldx), w [C][C][3] fp32, y NCHW fp32 [nb*T][C][HW]. */
+int v3d_time_mix_conv(const void* x, int64_t ldx, const void* w, const void* bias, void* y, int32_t nb, int32_t T,
+                      int64_t HW, int32_t C, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * EDM sampler arithmetic, fp32 (sampler.cu)

@@ -1,0 +1,171 @@
+"""Generate tests/golden/*.pt from the REAL reference modules and pin the oracle against them.
+
+TEST INFRASTRUCTURE; runs only in the build container (needs /root/reference):
+    python -m oracle.make_golden            # all fixtures
+    python -m oracle.make_golden unet_small # one fixture
+
+For every fixture the reference module (imported through oracle/reference_shim.py, weights from
+oracle/synth.py) is run on CPU fp32, the oracle restatement is run on the same inputs, and the script fails
+unless they agree to <= 2e-4 of the output scale.  Only the reference's outputs are stored.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+from . import ref_decoder, ref_sampling, ref_unet, reference_shim, synth
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+PIN_TOL = 2e-4
+
+
+def _pin(name: str, ref: torch.Tensor, ora: torch.Tensor) -> float:
+    scale = ref.abs().max().clamp_min(1e-6)
+    err = ((ref - ora).abs().max() / scale).item()
+    print(f"  pin {name}: max|ref-oracle|/max|ref| = {err:.3e}")
+    if not err <= PIN_TOL:
+        raise SystemExit(f"oracle does not reproduce the reference on {name}: {err}")
+    return err
+
+
+def _unet_case(ns, tag: str, model_channels: int, T: int, hw: int, wseed: int, sigma: float, manifest: dict):
+    kw = dict(reference_shim.V3D_UNET_KW)
+    kw["model_channels"] = model_channels
+    net = ns.video_model.VideoUNet(**kw).eval()
+    spec = ref_unet.UNetSpec(model_channels=model_channels)
+    shapes = ref_unet.unet_param_shapes(spec)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+    sd = synth.synth_state_dict(shapes, seed=wseed)
+    net.load_state_dict(sd)
+    x, c, uc = synth.synth_inputs(T, hw)
+    xin = torch.cat([torch.cat([x, x]), torch.cat([uc["concat"], c["concat"]])], 1)
+    ctx = torch.cat([uc["crossattn"], c["crossattn"]])
+    y = torch.cat([uc["vector"], c["vector"]])
+    ts = torch.full((2 * T,), 0.25 * torch.log(torch.tensor(sigma)).item())
+    ind = torch.zeros(2, T)
+    taps_ref = {}
+    hooks = []
+    want = ["input_blocks.1.0", "input_blocks.1.1", "input_blocks.3.0", "middle_block.1", "output_blocks.2.1",
+            "output_blocks.11.1"]
+    mods = dict(net.named_modules())
+    for w in want:
+        hooks.append(mods[w].register_forward_hook(lambda m, i, o, w=w: taps_ref.__setitem__(w, o.detach().clone())))
+    with torch.no_grad():
+        t0 = time.time()
+        ref = net(xin, ts, ctx, y, None, T, ind)
+        t_ref = time.time() - t0
+        taps_or = {}
+        ora = ref_unet.unet_forward(sd, spec, xin, ts, ctx, y, T, ind, taps=taps_or)
+    for h in hooks:
+        h.remove()
+    err = _pin(tag, ref, ora)
+    for w in want:
+        _pin(f"{tag}:{w}", taps_ref[w], taps_or[w])
+    blob = {"out": ref, "timesteps": ts}
+    for w in want:
+        # keep fixtures small: frames {0 (uc half), T (c half)}, every 8th channel, fp16
+        blob["tap:" + w] = taps_ref[w][[0, T]][:, ::8].half()
+    torch.save(blob, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="unet_forward", model_channels=model_channels, T=T, latent_hw=hw, weight_seed=wseed,
+                         input_seed=23, sigma=sigma, pin_err=err, ref_cpu_seconds=round(t_ref, 2),
+                         out_std=ref.std().item())
+    return net, sd, spec
+
+
+def _edm_step_case(ns, net, sd, spec, tag: str, T: int, hw: int, num_steps: int, manifest: dict):
+    """BASELINE.json configs[0]: EDM step(s) through the reference sampler/denoiser/wrapper around the UNet."""
+    x, c, uc = synth.synth_inputs(T, hw)
+    sampler = ns.sampling.EulerEDMSampler(
+        num_steps=num_steps,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                               "params": {"sigma_max": 700.0}},
+        guider_config={"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                       "params": {"max_scale": 3.5, "min_scale": 1.5, "num_frames": T}},
+        device="cpu")
+    den = ns.denoiser.Denoiser({"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"})
+    wrapped = ns.wrappers.OpenAIWrapper(net)
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    with torch.no_grad():
+        ref = sampler(lambda i, s, cc: den(wrapped, i, s, cc, **extra), x.clone(), cond=c, uc=uc)
+        ora = ref_sampling.euler_edm_sample(
+            lambda i, s, cc: ref_sampling.denoiser(
+                lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd, spec, xx, tt, cond, **kw), i, s, cc, **extra),
+            x.clone(), c, uc, num_steps, ref_sampling.guider_scale(1.5, 3.5, T), T)
+    err = _pin(tag, ref, ora)
+    torch.save({"out": ref}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="edm_sample", T=T, latent_hw=hw, num_steps=num_steps, min_scale=1.5, max_scale=3.5,
+                         sigma_max=700.0, pin_err=err, out_std=ref.std().item())
+    return ref
+
+
+def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, manifest: dict, z=None):
+    kw = dict(reference_shim.V3D_DECODER_KW)
+    kw["ch"] = ch
+    dec = ns.temporal_ae.VideoDecoder(**kw).eval()
+    spec = ref_decoder.DecoderSpec(ch=ch)
+    shapes = ref_decoder.decoder_param_shapes(spec)
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+    sd = synth.synth_state_dict(shapes, seed=wseed)
+    dec.load_state_dict(sd)
+    if z is None:
+        g = torch.Generator().manual_seed(77)
+        z = torch.randn(B, 4, hw, hw, generator=g)
+    with torch.no_grad():
+        t0 = time.time()
+        # decode_first_stage semantics (video_diffusion.py:182-210): z / scale_factor, one chunk of T frames
+        ref = dec(z / 0.18215, timesteps=T)
+        t_ref = time.time() - t0
+        ora = ref_decoder.decode_first_stage(sd, spec, z, n_samples_a_time=T) if B == T else \
+            ref_decoder.decoder_forward(sd, spec, z / 0.18215, T)
+    err = _pin(tag, ref, ora)
+    torch.save({"out": ref, "z": z}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="decode", ch=ch, T=T, B=B, latent_hw=hw, weight_seed=wseed, z_seed=77, pin_err=err,
+                         ref_cpu_seconds=round(t_ref, 2), out_std=ref.std().item())
+
+
+def main(argv):
+    OUT.mkdir(parents=True, exist_ok=True)
+    ns = reference_shim.load()
+    torch.set_num_threads(8)
+    mpath = OUT / "MANIFEST.json"
+    manifest = json.loads(mpath.read_text()) if mpath.exists() else {}
+    only = set(argv)
+
+    def want(tag):
+        return not only or tag in only
+
+    if want("unet_small") or want("edm_small"):
+        net, sd, spec = _unet_case(ns, "unet_small", 64, T=4, hw=32, wseed=1, sigma=3.0, manifest=manifest)
+        _edm_step_case(ns, net, sd, spec, "edm_small", T=4, hw=32, num_steps=3, manifest=manifest)
+    if want("unet_small_t18"):
+        _unet_case(ns, "unet_small_t18", 64, T=18, hw=16, wseed=2, sigma=40.0, manifest=manifest)
+    if want("unet_full") or want("edm_full_step"):
+        # BASELINE.json configs[0]: full-width VideoUNet, latent 4x32x32, T=4, 1 EDM step, fp32 CPU
+        net, sd, spec = _unet_case(ns, "unet_full", 320, T=4, hw=32, wseed=3, sigma=3.0, manifest=manifest)
+        _edm_step_case(ns, net, sd, spec, "edm_full_step", T=4, hw=32, num_steps=1, manifest=manifest)
+    if want("decoder_small"):
+        _decoder_case(ns, "decoder_small", 64, T=3, B=3, hw=16, wseed=4, manifest=manifest)
+    if want("decoder_small_2videos"):
+        _decoder_case(ns, "decoder_small_2videos", 64, T=2, B=4, hw=8, wseed=5, manifest=manifest)
+    if want("decoder_full"):
+        _decoder_case(ns, "decoder_full", 128, T=2, B=2, hw=16, wseed=6, manifest=manifest)
+    # integer / index paths: sigma schedule and guider scale, bit-exact
+    if want("schedule"):
+        disc = ns.discretizer.EDMDiscretization(sigma_max=700.0)
+        blob = {f"sigmas_{n}": disc(n) for n in (1, 10, 25, 50)}
+        blob["guider_scale_18"] = ns.guiders.LinearPredictionGuider(max_scale=3.5, min_scale=1.0, num_frames=18).scale
+        for n in (1, 10, 25, 50):
+            assert torch.equal(blob[f"sigmas_{n}"], ref_sampling.edm_sigmas(n))
+        assert torch.equal(blob["guider_scale_18"], ref_sampling.guider_scale(1.0, 3.5, 18))
+        torch.save(blob, OUT / "schedule.pt")
+        manifest["schedule"] = dict(kind="schedule", note="EDMDiscretization(sigma_max=700)(n) incl. appended 0")
+    mpath.write_text(json.dumps(manifest, indent=1, sort_keys=True))
+    print("wrote", sorted(p.name for p in OUT.glob("*")))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

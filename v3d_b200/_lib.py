@@ -49,6 +49,7 @@ SIGNATURES = {
     "v3d_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "v3d_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
     "v3d_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp]),
+    "v3d_softmax_rows_f32": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),
     # attention.cu
     "v3d_attention_spatial": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "v3d_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
@@ -58,9 +59,10 @@ SIGNATURES = {
     "v3d_im2col3x3": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "v3d_nchw_f32_to_nhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "v3d_nhwc_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp]),
-    "v3d_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "v3d_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp]),
     "v3d_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "v3d_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "v3d_time_mix_conv": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     # sampler.cu
     "v3d_edm_scale_input": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "v3d_edm_denoise_combine": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),

@@ -116,7 +116,8 @@ constexpr int kSlChunk = 8;  // rows of x processed per pass over the weight row
 
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W, const float* __restrict__ bias,
-                    float* __restrict__ y, int M, int K, int N, int act_in, int act_out, int accumulate) {
+                    float* __restrict__ y, int M, int K, int N, int act_in, int act_out, int accumulate,
+                    long long ldx, long long ldy) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -139,8 +140,8 @@ small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W, con
 #pragma unroll
       for (int i = 0; i < kSlChunk; ++i) {
         if (m0 + i < M) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * K + k));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * K + k + 4));
+          const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * ldx + k));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * ldx + k + 4));
           float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           if (act_in == V3D_ACT_SILU) {
 #pragma unroll
@@ -157,7 +158,7 @@ small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W, con
       if (lane == 0 && m0 + i < M) {
         float v = s + bv;
         if (act_out == V3D_ACT_SILU) v = v / (1.0f + expf(-v));
-        float* o = y + static_cast<long long>(m0 + i) * N + n;
+        float* o = y + static_cast<long long>(m0 + i) * ldy + n;
         *o = accumulate ? *o + v : v;
       }
     }
@@ -187,6 +188,31 @@ __global__ void add_rows_kernel(const float* __restrict__ a, const float* __rest
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     o[i] = a[i] + b[i];
+}
+
+// ---------------- AE3DConv time_mix_conv: Conv3d C->C (C <= 4), k=(3,1,1), pad (1,0,0), NHWC fp32 in, NCHW fp32 out
+__global__ void time_mix_conv_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ y, int nb, int T,
+                                     long long HW, int C) {
+  const long long total = static_cast<long long>(nb) * T * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i % HW;
+    const long long f = i / HW;  // frame index b*T + t
+    const int t = static_cast<int>(f % T);
+    float acc[4];
+    for (int co = 0; co < C; ++co) acc[co] = bias[co];
+    for (int tap = 0; tap < 3; ++tap) {
+      const int tt = t + tap - 1;
+      if (tt < 0 || tt >= T) continue;
+      const float* xp = x + ((f + tap - 1) * HW + p) * ldx;
+      for (int ci = 0; ci < C; ++ci) {
+        const float v = xp[ci];
+        for (int co = 0; co < C; ++co) acc[co] = fmaf(w[(co * C + ci) * 3 + tap], v, acc[co]);
+      }
+    }
+    for (int co = 0; co < C; ++co) y[(f * C + co) * HW + p] = acc[co];
+  }
 }
 
 }  // namespace v3d
@@ -274,15 +300,17 @@ int v3d_nhwc_to_nchw_f32(const void* x, void* y, int32_t N, int32_t C, int32_t H
  * emb_layers (openaimodel.py:291-297), time_pos_embed (video_attention.py:220-224,275), and the
  * single-token cross-attention collapse to_out(to_v(ctx)) (attention.py:277-283 with one key). */
 int v3d_small_linear(const void* x, const void* W, const void* bias, void* y, int32_t M, int32_t K, int32_t N,
-                     int32_t act_in, int32_t act_out, int32_t accumulate, void* stream) {
-  if (!x || !W || !y || M <= 0 || M > kSlMaxM || K % 8 != 0 || N <= 0) {
+                     int32_t act_in, int32_t act_out, int32_t accumulate, int64_t ldx, int64_t ldy, void* stream) {
+  if (ldx <= 0) ldx = K;
+  if (ldy <= 0) ldy = N;
+  if (!x || !W || !y || M <= 0 || M > kSlMaxM || K % 8 != 0 || N <= 0 || ldx % 4 != 0) {
     set_error("v3d_small_linear: bad args M=%d K=%d N=%d", M, K, N);
     return V3D_ERR_BAD_ARG;
   }
   const int warps = 8;
   small_linear_kernel<<<(N + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(x), static_cast<const bf16*>(W), static_cast<const float*>(bias),
-      static_cast<float*>(y), M, K, N, act_in, act_out, accumulate);
+      static_cast<float*>(y), M, K, N, act_in, act_out, accumulate, ldx, ldy);
   V3D_CHECK_LAUNCH("small_linear_kernel");
   return V3D_OK;
 }
@@ -297,6 +325,23 @@ int v3d_timestep_embedding(const void* t, void* out, int32_t n, int32_t dim, flo
                               static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(t),
                                                                    static_cast<float*>(out), n, dim, max_period);
   V3D_CHECK_LAUNCH("timestep_embedding_kernel");
+  return V3D_OK;
+}
+
+/* AE3DConv.time_mix_conv (temporal_ae.py:94-107): Conv3d(C, C, (3,1,1), pad (1,0,0)) across the frames of each
+ * video, C <= 4. x: NHWC fp32 [nb*T*HW][ldx] (first C channels), w: [C][C][3] fp32, y: NCHW fp32 [nb*T][C][HW]. */
+int v3d_time_mix_conv(const void* x, int64_t ldx, const void* w, const void* bias, void* y, int32_t nb, int32_t T,
+                      int64_t HW, int32_t C, void* stream) {
+  if (!x || !w || !bias || !y || C <= 0 || C > 4 || nb <= 0 || T <= 0 || HW <= 0) {
+    set_error("v3d_time_mix_conv: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  time_mix_conv_kernel<<<blocks_for(static_cast<long long>(nb) * T * HW, 256), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ldx,
+                                                              static_cast<const float*>(w),
+                                                              static_cast<const float*>(bias),
+                                                              static_cast<float*>(y), nb, T, HW, C);
+  V3D_CHECK_LAUNCH("time_mix_conv_kernel");
   return V3D_OK;
 }
 

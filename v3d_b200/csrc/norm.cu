@@ -265,6 +265,54 @@ softmax_rows_kernel(bf16* __restrict__ x, int n, float scale) {
   }
 }
 
+// fp32 scores -> bf16 probabilities (separate buffers): keeps the decoder's 4096-wide softmax input in fp32.
+__global__ void __launch_bounds__(256)
+softmax_rows_f32_kernel(const float* __restrict__ x, bf16* __restrict__ y, int n, float scale) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* row = x + static_cast<long long>(blockIdx.x) * n;
+  bf16* orow = y + static_cast<long long>(blockIdx.x) * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = n >> 2;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 f = *reinterpret_cast<const float4*>(row + i * 4);
+    m = fmaxf(m, fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w)));
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i) t = fmaxf(t, red[i]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast * scale;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 f = *reinterpret_cast<const float4*>(row + i * 4);
+    s += __expf(f.x * scale - m) + __expf(f.y * scale - m) + __expf(f.z * scale - m) + __expf(f.w * scale - m);
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    bcast = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 f = *reinterpret_cast<const float4*>(row + i * 4);
+    *reinterpret_cast<uint2*>(orow + i * 4) =
+        make_uint2(pack_bf16x2(__expf(f.x * scale - m) * inv, __expf(f.y * scale - m) * inv),
+                   pack_bf16x2(__expf(f.z * scale - m) * inv, __expf(f.w * scale - m) * inv));
+  }
+}
+
 static int pick_rows_per_cta(long long rows_per_sample, int nsamples) {
   // aim for >= ~4 waves of CTAs over the SMs while keeping at least 32 rows per CTA
   const long long target = 4LL * num_sms();
@@ -359,6 +407,18 @@ int v3d_softmax_rows(void* x, int64_t rows, int32_t n, float scale, void* stream
   softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<bf16*>(x), n, scale);
   V3D_CHECK_LAUNCH("softmax_rows_kernel");
+  return V3D_OK;
+}
+
+/* softmax(scale * x) from fp32 scores to bf16 probabilities (decoder AttnBlock, model.py:190-192). */
+int v3d_softmax_rows_f32(const void* x, void* y, int64_t rows, int32_t n, float scale, void* stream) {
+  if (!x || !y || n % 4 != 0 || rows <= 0 || rows > 0x7fffffffLL) {
+    set_error("v3d_softmax_rows_f32: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  softmax_rows_f32_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<bf16*>(y), n, scale);
+  V3D_CHECK_LAUNCH("softmax_rows_f32_kernel");
   return V3D_OK;
 }
 

@@ -127,6 +127,22 @@ def softmax_rows(x: torch.Tensor, rows: int, n: int, scale: float = 1.0) -> torc
     return x
 
 
+def softmax_rows_f32(x: torch.Tensor, y: torch.Tensor, rows: int, n: int, scale: float = 1.0) -> torch.Tensor:
+    _need(x, torch.float32, "softmax x")
+    _need(y, torch.bfloat16, "softmax y")
+    _lib.check(_lib.load().v3d_softmax_rows_f32(x.data_ptr(), y.data_ptr(), rows, n, scale, _stream()),
+               "v3d_softmax_rows_f32")
+    return y
+
+
+def time_mix_conv(x: torch.Tensor, ldx: int, w: torch.Tensor, bias: torch.Tensor, y: torch.Tensor, nb: int, t: int,
+                  hw: int, c: int) -> torch.Tensor:
+    _need(x, torch.float32, "time_mix_conv x")
+    _lib.check(_lib.load().v3d_time_mix_conv(x.data_ptr(), ldx, w.data_ptr(), bias.data_ptr(), y.data_ptr(), nb, t,
+                                             hw, c, _stream()), "v3d_time_mix_conv")
+    return y
+
+
 def attention_spatial(qkv: torch.Tensor, out: torch.Tensor, nbatch: int, ntok: int, nheads: int,
                       scale: float) -> torch.Tensor:
     """qkv: [nbatch*ntok, 3*C] packed (q | k | v), out: [nbatch*ntok, C]."""
@@ -188,13 +204,21 @@ def nhwc_to_nchw_f32(x: torch.Tensor, y: torch.Tensor, n: int, c: int, hw: int, 
 
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *,
                  act_in: int = ACT_NONE, act_out: int = ACT_NONE, accumulate: bool = False) -> torch.Tensor:
+    """y[M,N] fp32 = act_out(act_in(x) @ w.T + bias). x and y may be column slices of wider row-major
+    buffers (their row strides are taken from the tensors); M is processed in chunks of 64 rows."""
     _need(x, torch.float32, "small_linear x")
     _need(w, torch.bfloat16, "small_linear w")
     m, k = x.shape
     n = w.shape[0]
-    _lib.check(_lib.load().v3d_small_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), m, k, n,
-                                            act_in, act_out, 1 if accumulate else 0, _stream()),
-               "v3d_small_linear")
+    if x.stride(1) != 1 or y.stride(1) != 1 or w.shape[1] != k or not w.is_contiguous():
+        raise RuntimeError("small_linear: bad strides/shapes")
+    ldx, ldy = x.stride(0), y.stride(0)
+    lib = _lib.load()
+    for m0 in range(0, m, 64):
+        mm = min(64, m - m0)
+        _lib.check(lib.v3d_small_linear(x.data_ptr() + m0 * ldx * 4, w.data_ptr(), _ptr(bias),
+                                        y.data_ptr() + m0 * ldy * 4, mm, k, n, act_in, act_out,
+                                        1 if accumulate else 0, ldx, ldy, _stream()), "v3d_small_linear")
     return y
 
 
