@@ -1,0 +1,98 @@
+"""CPU tests of the oracle itself: the restatement must reproduce the committed outputs of the REAL reference
+modules (tests/golden, written by oracle/make_golden.py) on this machine too."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import ref_decoder, ref_sampling, ref_unet, synth
+
+GOLD = Path(__file__).resolve().parent / "golden"
+MANIFEST = json.loads((GOLD / "MANIFEST.json").read_text())
+
+
+def _close(a, b, tol=2e-4):
+    return ((a - b).abs().max() / b.abs().max()).item() <= tol
+
+
+def _unet_inputs(T, hw):
+    x, c, uc = synth.synth_inputs(T, hw)
+    xin = torch.cat([torch.cat([x, x]), torch.cat([uc["concat"], c["concat"]])], 1)
+    return x, c, uc, xin, torch.cat([uc["crossattn"], c["crossattn"]]), torch.cat([uc["vector"], c["vector"]])
+
+
+@pytest.mark.parametrize("tag", ["unet_small", "unet_small_t18"])
+def test_oracle_unet_vs_reference_golden(tag):
+    m = MANIFEST[tag]
+    gold = torch.load(GOLD / f"{tag}.pt")
+    spec = ref_unet.UNetSpec(model_channels=m["model_channels"])
+    sd = synth.synth_state_dict(ref_unet.unet_param_shapes(spec), seed=m["weight_seed"])
+    T = m["T"]
+    _, _, _, xin, ctx, y = _unet_inputs(T, m["latent_hw"])
+    taps = {}
+    with torch.no_grad():
+        out = ref_unet.unet_forward(sd, spec, xin, gold["timesteps"], ctx, y, T, torch.zeros(2, T), taps=taps)
+    assert _close(out, gold["out"])
+    for k, v in gold.items():
+        if k.startswith("tap:"):
+            assert _close(taps[k[4:]][[0, T]][:, ::8], v.float(), tol=2e-3)  # fixture taps are fp16
+
+
+def test_oracle_edm_sampler_vs_reference_golden():
+    m, mu = MANIFEST["edm_small"], MANIFEST["unet_small"]
+    gold = torch.load(GOLD / "edm_small.pt")
+    spec = ref_unet.UNetSpec(model_channels=mu["model_channels"])
+    sd = synth.synth_state_dict(ref_unet.unet_param_shapes(spec), seed=mu["weight_seed"])
+    T = m["T"]
+    x, c, uc = synth.synth_inputs(T, m["latent_hw"])
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    with torch.no_grad():
+        out = ref_sampling.euler_edm_sample(
+            lambda i, s, cc: ref_sampling.denoiser(
+                lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd, spec, xx, tt, cond, **kw), i, s, cc, **extra),
+            x.clone(), c, uc, m["num_steps"], ref_sampling.guider_scale(m["min_scale"], m["max_scale"], T), T)
+    assert _close(out, gold["out"])
+
+
+@pytest.mark.parametrize("tag", ["decoder_small", "decoder_small_2videos", "decoder_full"])
+def test_oracle_decoder_vs_reference_golden(tag):
+    m = MANIFEST[tag]
+    gold = torch.load(GOLD / f"{tag}.pt")
+    spec = ref_decoder.DecoderSpec(ch=m["ch"])
+    sd = synth.synth_state_dict(ref_decoder.decoder_param_shapes(spec), seed=m["weight_seed"])
+    with torch.no_grad():
+        out = ref_decoder.decoder_forward(sd, spec, gold["z"] / 0.18215, m["T"])
+    assert _close(out, gold["out"])
+
+
+def test_oracle_schedule_bit_exact():
+    gold = torch.load(GOLD / "schedule.pt")
+    for n in (1, 10, 25, 50):
+        s = ref_sampling.edm_sigmas(n)
+        assert torch.equal(s, gold[f"sigmas_{n}"])
+        assert s.shape[0] == n + 1 and s[-1] == 0 and bool((s[:-1][1:] < s[:-1][:-1]).all() if n > 1 else True)
+    assert torch.equal(ref_sampling.guider_scale(1.0, 3.5, 18), gold["guider_scale_18"])
+
+
+def test_oracle_cfg_order_and_chunking():
+    """Index paths: [uc; c] ordering, per-frame scale broadcast, decode chunk boundaries."""
+    T = 3
+    x = torch.arange(T * 2.0).reshape(T, 2)
+    c = {"vector": torch.ones(T, 1), "crossattn": torch.ones(T, 1, 2), "concat": torch.ones(T, 2)}
+    uc = {k: torch.zeros_like(v) for k, v in c.items()}
+    x2, s2, c2 = ref_sampling.guider_prepare_inputs(x, torch.ones(T), c, uc)
+    assert torch.equal(x2[:T], x) and torch.equal(x2[T:], x)
+    assert c2["vector"][:T].sum() == 0 and c2["vector"][T:].sum() == T  # uc FIRST
+    den = torch.cat([torch.zeros(T, 2), torch.ones(T, 2)])
+    out = ref_sampling.guider_combine(den, torch.tensor([[1.0, 2.0, 3.0]]), T)
+    assert torch.equal(out, torch.tensor([[1.0, 1.0], [2.0, 2.0], [3.0, 3.0]]))
+    spec = ref_decoder.DecoderSpec(ch=32)
+    sd = synth.synth_state_dict(ref_decoder.decoder_param_shapes(spec), seed=9)
+    z = torch.randn(4, 4, 8, 8)
+    with torch.no_grad():
+        whole = ref_decoder.decode_first_stage(sd, spec, z, 4)
+        halves = ref_decoder.decode_first_stage(sd, spec, z, 2)
+        ref_halves = torch.cat([ref_decoder.decoder_forward(sd, spec, z[:2] / 0.18215, 2),
+                                ref_decoder.decoder_forward(sd, spec, z[2:] / 0.18215, 2)])
+    assert torch.allclose(halves, ref_halves, atol=1e-5) and not torch.allclose(whole, halves, atol=1e-3)

@@ -86,6 +86,31 @@ class KernelModule(nn.Module):
     def _pack(self, dev: torch.device) -> dict:  # pragma: no cover - abstract
         raise NotImplementedError
 
+    @torch.no_grad()
+    def init_random_(self, device, seed: int = 0) -> "KernelModule":
+        """Materialise every parameter directly on `device` with non-degenerate random values (conv/linear
+        weights N(0, 1/fan_in), biases N(0, 0.05^2), norm scales 1 + N(0, 0.1^2), mix factors N(0, 1)).
+        For synthetic-weight benchmarking of a module built under `torch.device("meta")`: no 6 GB host copy."""
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        for name, p in list(self.named_parameters()):
+            shape = tuple(p.shape)
+            if name.endswith("mix_factor"):
+                val = torch.randn(shape, device=device, generator=gen)
+            elif len(shape) > 1:
+                val = torch.randn(shape, device=device, generator=gen) * (1.0 / math.sqrt(math.prod(shape[1:])))
+            elif name.endswith(".weight"):
+                val = 1.0 + 0.1 * torch.randn(shape, device=device, generator=gen)
+            else:
+                val = 0.05 * torch.randn(shape, device=device, generator=gen)
+            parts = name.split(".")
+            mod = self
+            for part in parts[:-1]:
+                mod = mod._modules[part]
+            mod._parameters[parts[-1]] = nn.Parameter(val, requires_grad=False)
+        self._invalidate()
+        return self
+
     # ---- packing helpers -------------------------------------------------------------------
     @staticmethod
     def _bf(t: torch.Tensor) -> torch.Tensor:
@@ -383,8 +408,11 @@ class VideoUNet(KernelModule):
         video_model.py:439) and mix_factor = merge_factor."""
         gen = torch.Generator(device="cpu")
         gen.manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        on_meta = torch.empty(0).device.type == "meta"  # `with torch.device("meta")`: shapes only, no values
         for key, shape in self.param_shapes().items():
-            if key.endswith("mix_factor"):
+            if on_meta:
+                val = torch.empty(shape)
+            elif key.endswith("mix_factor"):
                 val = torch.full(shape, float(self.merge_factor))
             elif key.endswith(self.ZERO_INIT_SUFFIXES):
                 val = torch.zeros(shape)
@@ -733,7 +761,7 @@ class VideoUNet(KernelModule):
                 ops.copy_channels(cur, ch, cat.data_ptr(), ch + sc, rows, ch)
                 ops.copy_channels(skip, sc, cat.data_ptr() + ch * 2, ch + sc, rows, sc)
                 cur, ch = cat, ch + sc
-            if self.debug_taps is not None and st.name in self.debug_taps and st.kind in ("res", "attn", "down"):
+            if self.debug_taps is not None and st.name in self.debug_taps and st.kind in ("res", "attn", "down", "up"):
                 tap = torch.empty(B, ch, h, w, device=dev, dtype=torch.float32)
                 ops.nhwc_to_nchw_f32(cur, tap, B, ch, h * w, ch)
                 self.debug_taps[st.name] = tap
