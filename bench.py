@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — view-frames/sec of the V3D denoising hot path (EulerEDMSampler -> VideoUNet -> VideoDecoder).
+
+    python bench.py --gpus N --steps K --warmup W            # B200-native arm (this repo's kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+One "step" = the whole hot path for one image: T=18 views, 512x512 (latent 4x64x64), 25 Euler-EDM steps with CFG
+(B=36 per UNet call) + first-stage decode of the T frames — BASELINE.json configs[1] (V3D_512).  With N GPUs each
+rank processes its own image (weak scaling, no data-path collective; the only exchange is the final uint8 frame
+gather).  Prints ONE JSON line (rank 0).  Synthetic data, random-init weights of the V3D_512 architecture.
+
+Timed regions (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks):
+  value : inputs already resident in HBM
+  e2e   : through the public API with pinned HOST buffers, H2D of noise+conditioning and D2H of the uint8 frames
+          inside the timed region.
+`roofline` describes the dominant kernel family (the tcgen05 GEMM / implicit conv kernel): algorithmic FLOPs of its
+launches in one step / their summed CUDA-event durations, against MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic FLOPs of the reference modules (FlopCounterMode on the reference, 2*MAC, CFG-batched)
+F_UNET_TF = {14: 35.542, 18: 45.677, 24: 60.884, 25: 63.419}
+F_DEC_TF = {14: 42.599, 18: 54.771, 24: 73.028, 25: 76.070}
+FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+
+
+def work_tf(T: int, S: int, latent: int) -> float:
+    fu = F_UNET_TF.get(T, 2.537 * T)
+    fd = F_DEC_TF.get(T, 3.043 * T)
+    return (S * fu + fd) * (latent / 64.0) ** 2
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return d, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if not (t0 <= ts <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port timed on host cores, on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuReference:
+    """Oracle port (oracle/, kind "port") of the reference path. One `sample()` = one CFG-batched UNet forward
+    (B = 2T) at T frames on a latent_u x latent_u latent + one first-stage decode of T frames on a
+    latent_d x latent_d latent, fp32, all host threads; extrapolated to the full workload by pixel count
+    (the attention N^2 term is under-counted by this scaling, which favours the CPU number)."""
+
+    def __init__(self, T: int, S: int, latent: int, latent_u: int = 32, latent_d: int = 16):
+        import torch
+        from oracle import ref_decoder, ref_unet  # the one place bench.py executes oracle/: the timed baseline
+
+        self.torch, self.ref_unet, self.ref_decoder = torch, ref_unet, ref_decoder
+        self.T, self.S, self.latent, self.lu, self.ld = T, S, latent, min(latent_u, latent), min(latent_d, latent)
+        self.threads = _cpu_threads()
+        torch.set_num_threads(self.threads)
+        self.spec_u = ref_unet.UNetSpec()
+        self.spec_d = ref_decoder.DecoderSpec()
+        g = torch.Generator().manual_seed(0)
+
+        def rnd(shape, key):
+            shape = tuple(shape)
+            if len(shape) > 1:
+                fan = 1
+                for d in shape[1:]:
+                    fan *= d
+                return torch.empty(shape).normal_(0, fan ** -0.5, generator=g)
+            if key.endswith(".weight"):
+                return torch.ones(shape)
+            return torch.zeros(shape)
+
+        self.sd_u = {k: rnd(s, k) for k, s in ref_unet.unet_param_shapes(self.spec_u).items()}
+        self.sd_d = {k: rnd(s, k) for k, s in ref_decoder.decoder_param_shapes(self.spec_d).items()}
+        B = 2 * T
+        self.xin = torch.randn(B, 8, self.lu, self.lu, generator=g)
+        self.ts = torch.full((B,), 0.3)
+        self.ctx = torch.randn(B, 1, 1024, generator=g)
+        self.y = torch.randn(B, 768, generator=g)
+        self.ind = torch.zeros(2, T)
+        self.z = torch.randn(T, 4, self.ld, self.ld, generator=g)
+
+    def sample(self):
+        torch = self.torch
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            self.ref_unet.unet_forward(self.sd_u, self.spec_u, self.xin, self.ts, self.ctx, self.y, self.T, self.ind)
+            t1 = time.perf_counter()
+            self.ref_decoder.decoder_forward(self.sd_d, self.spec_d, self.z, self.T)
+            t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    def frames_per_sec(self, t_unet: float, t_dec: float) -> float:
+        ku = (self.latent / self.lu) ** 2
+        kd = (self.latent / self.ld) ** 2
+        return self.T / (self.S * t_unet * ku + t_dec * kd)
+
+    def describe(self) -> str:
+        return (f"oracle port fp32, {self.threads} threads: 1 CFG-batched UNet forward (B={2 * self.T}, T={self.T}, "
+                f"latent {self.lu}x{self.lu}) + 1 decode (T={self.T}, latent {self.ld}x{self.ld}); extrapolated to "
+                f"latent {self.latent}x{self.latent} by pixel count and to {self.S} EDM steps (steps are cost-identical)")
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference(args.frames, args.edm_steps, args.latent)
+    for _ in range(args.warmup):
+        ref.sample()
+    tu = td = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = ref.sample()
+        tu += a
+        td += b
+    wall = time.perf_counter() - t0
+    tu, td = tu / args.steps, td / args.steps
+    v = ref.frames_per_sec(tu, td)
+    line = {
+        "impl": "reference", "metric": "view-frames/sec", "value": v, "unit": "view-frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": v, "unit": "view-frames/s", "cores": ref.threads, "kind": "port",
+                         "sample": ref.describe(), "t_unet_sample_s": tu, "t_decode_sample_s": td},
+        "e2e": {"value": v, "unit": "view-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, where: str) -> dict:
+    return {"workload": f"V3D_512: 1 image -> {args.frames} views, {args.latent * 8}x{args.latent * 8}, "
+                        f"{args.edm_steps} Euler-EDM steps (CFG, B={2 * args.frames}) + first-stage decode; one image per GPU",
+            "frames": args.frames, "edm_steps": args.edm_steps, "latent": [4, args.latent, args.latent],
+            "cfg_scale": [args.min_cfg, args.max_cfg], "sigma_max": 700.0, "decode_chunk": args.frames,
+            "parallelism": f"image-dp{args.gpus}" if where != "cpu" else "host-cpu",
+            "l2_policy": "working set per step (3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
+            "weights": "random-init (seeded), zero-init modules re-randomised"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_native(args) -> None:
+    import torch
+
+    from v3d_b200 import engine, ops, parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback for the product path")
+    rank, local_rank, world = parallel.init()
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    T, S, L = args.frames, args.edm_steps, args.latent
+
+    cfg = engine.v3d_512_config(num_frames=T, num_steps=S, min_cfg=args.min_cfg, max_cfg=args.max_cfg)
+    with torch.device("meta"):
+        eng = engine.DiffusionEngine(**cfg)
+    eng.model.diffusion_model.init_random_(dev, seed=100 + rank)
+    eng.first_stage_model.decoder.init_random_(dev, seed=200 + rank)
+    eng.eval()
+
+    # synthetic inputs in pinned host memory (one image per rank)
+    g = torch.Generator().manual_seed(23 + rank)
+    host = {
+        "x": torch.randn(T, 4, L, L, generator=g).pin_memory(),
+        "c.crossattn": torch.randn(1, 1, 1024, generator=g).repeat(T, 1, 1).pin_memory(),
+        "c.concat": torch.randn(1, 4, L, L, generator=g).repeat(T, 1, 1, 1).pin_memory(),
+        "c.vector": torch.randn(T, 768, generator=g).pin_memory(),
+    }
+    host["uc.crossattn"] = torch.zeros_like(host["c.crossattn"]).pin_memory()
+    host["uc.concat"] = torch.zeros_like(host["c.concat"]).pin_memory()
+    host["uc.vector"] = host["c.vector"].clone().pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    frames_host = torch.empty(T, 8 * L, 8 * L, 3, dtype=torch.uint8).pin_memory()
+    d2h_bytes = frames_host.numel()
+
+    def upload():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        c = {k[2:]: d[k] for k in d if k.startswith("c.")}
+        uc = {k[3:]: d[k] for k in d if k.startswith("uc.")}
+        return d["x"], c, uc
+
+    def hot_path(x, c, uc):
+        """The public API call a user makes: sampler loop + decode, then the uint8 THWC wire format."""
+        img = eng.sample_views(x, c, uc, num_frames=T, decoding_t=T)       # [T,3,H,W] fp32
+        u8 = torch.empty(T, 8 * L, 8 * L, 3, device=dev, dtype=torch.uint8)
+        return ops.frames_nchw_to_u8(img.contiguous(), u8)
+
+    x_res, c_res, uc_res = upload()
+    torch.cuda.synchronize()
+
+    def step_resident():
+        return hot_path(x_res.clone(), c_res, uc_res)
+
+    def step_e2e():
+        x, c, uc = upload()
+        u8 = hot_path(x, c, uc)
+        frames_host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return frames_host
+
+    def timed(fn, k):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        w0 = time.time()
+        ev0.record()
+        for _ in range(k):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        w1 = time.time()
+        parallel.barrier()
+        secs = parallel.max_over_ranks(ev0.elapsed_time(ev1) / 1000.0, dev)
+        return secs, ops.launch_count() - l0, (w0, w1)
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    secs, launches, (w0, w1) = timed(step_resident, args.steps)
+    clk = clocks.stop(w0, w1) if rank == 0 else None
+
+    step_e2e()  # warm the e2e-only pieces (pinned copies)
+    secs_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel family: instrument every tensor-core GEMM/conv launch of ONE step
+    records = []
+    orig_gemm = ops.gemm
+
+    def probed(a, w, out, **kw):
+        K, N = kw["K"], kw["N"]
+        rows = kw["rows_per_batch"] * kw.get("batch", 1)
+        taps = 9 if kw.get("conv") is not None else kw.get("ntaps", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_gemm(a, w, out, **kw)
+        e1.record()
+        records.append((2.0 * rows * N * K * taps, e0, e1))
+        return r
+
+    ops.gemm = probed
+    try:
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        pe0.record()
+        step_resident()
+        pe1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig_gemm
+    gemm_flops = sum(r[0] for r in records)
+    gemm_ms = sum(r[1].elapsed_time(r[2]) for r in records)
+    probe_ms = pe0.elapsed_time(pe1)
+
+    peaks, peak_src = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
+    n_img = world
+    value = n_img * T * args.steps / secs
+    e2e_value = n_img * T * args.steps / secs_e2e
+    model_tf = work_tf(T, S, L)
+
+    line = {
+        "metric": "view-frames/sec", "value": value, "unit": "view-frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, "gpu"),
+        "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000.0 * secs_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {
+            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / temporal conv / implicit 3x3 conv)",
+            "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": (gemm_flops / (gemm_ms * 1e-3) / 1e12) / peak_tf if gemm_ms > 0 else None,
+            "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+            "launches_per_step": len(records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
+            "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
+            "model": {"reference_accounting_tflop_per_step": model_tf,
+                      "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
+        },
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(T, S, L)
+        tu, td = ref.sample()
+        line["cpu_baseline"] = {"value": ref.frames_per_sec(tu, td), "unit": "view-frames/s", "cores": ref.threads,
+                                "kind": "port", "sample": ref.describe(), "t_unet_sample_s": tu,
+                                "t_decode_sample_s": td}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--frames", type=int, default=18)
+    ap.add_argument("--edm-steps", type=int, default=25)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--min-cfg", type=float, default=3.5)
+    ap.add_argument("--max-cfg", type=float, default=3.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        print("warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

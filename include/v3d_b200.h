@@ -174,6 +174,8 @@ int v3d_euler_step(const void* x, const void* den, const void* sigma_hat, const 
                    int32_t nsamples, int64_t per_sample, void* stream);
 /* clamp((x+1)/2,0,1)*255 -> uint8 THWC from the decoder's NHWC output (scripts/pub/V3D_512.py:286-303). */
 int v3d_decode_to_u8(const void* x, int64_t ldx, int32_t src_fp32, void* y, int64_t npix, void* stream);
+/* same, from NCHW fp32 frames [T][3][HW] (decode_first_stage's return layout) to uint8 [T][HW][3]. */
+int v3d_frames_nchw_to_u8(const void* x, void* y, int32_t T, int64_t HW, void* stream);
 
 #ifdef __cplusplus
 }

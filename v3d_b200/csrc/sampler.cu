@@ -81,6 +81,20 @@ __global__ void decode_to_u8_kernel(const T* __restrict__ x, long long ldx, uint
   }
 }
 
+// same wire format straight from the decoder's NCHW fp32 output: y[t][p][c] = u8(x[t][c][p])
+__global__ void frames_nchw_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int T, long long HW) {
+  const long long total = static_cast<long long>(T) * HW * 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % 3);
+    const long long p = (i / 3) % HW;
+    const long long t = i / (3 * HW);
+    float v = (x[(t * 3 + c) * HW + p] + 1.0f) / 2.0f;
+    v = fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f;
+    y[i] = static_cast<uint8_t>(v);
+  }
+}
+
 }  // namespace v3d
 
 using namespace v3d;
@@ -160,6 +174,20 @@ int v3d_decode_to_u8(const void* x, int64_t ldx, int32_t src_fp32, void* y, int6
     decode_to_u8_kernel<bf16><<<ew_blocks(npix * 3), 256, 0, st>>>(static_cast<const bf16*>(x), ldx,
                                                                    static_cast<uint8_t*>(y), npix);
   V3D_CHECK_LAUNCH("decode_to_u8_kernel");
+  return V3D_OK;
+}
+
+/* The same conversion from the decoder's NCHW fp32 frames [T][3][HW] -> uint8 [T][HW][3]
+ * (rearrange "t c h w -> t h w c" + clamp + *255 + astype(uint8), scripts/pub/V3D_512.py:286-303). */
+int v3d_frames_nchw_to_u8(const void* x, void* y, int32_t T, int64_t HW, void* stream) {
+  if (!x || !y || T <= 0 || HW <= 0) {
+    set_error("v3d_frames_nchw_to_u8: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  frames_nchw_to_u8_kernel<<<ew_blocks(static_cast<long long>(T) * HW * 3), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x),
+                                                                  static_cast<uint8_t*>(y), T, HW);
+  V3D_CHECK_LAUNCH("frames_nchw_to_u8_kernel");
   return V3D_OK;
 }
 

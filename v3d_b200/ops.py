@@ -259,3 +259,13 @@ def decode_to_u8(x: torch.Tensor, ldx: int, y: torch.Tensor, npix: int):
     _lib.check(_lib.load().v3d_decode_to_u8(x.data_ptr(), ldx, 1 if x.dtype == torch.float32 else 0,
                                             y.data_ptr(), npix, _stream()), "v3d_decode_to_u8")
     return y
+
+
+def frames_nchw_to_u8(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """[T,3,H,W] fp32 in [-1,1] -> [T,H,W,3] uint8 (the wire format of sample_one)."""
+    _need(x, torch.float32, "frames")
+    t, c, h, w = x.shape
+    assert c == 3 and x.is_contiguous() and y.dtype == torch.uint8
+    _lib.check(_lib.load().v3d_frames_nchw_to_u8(x.data_ptr(), y.data_ptr(), t, h * w, _stream()),
+               "v3d_frames_nchw_to_u8")
+    return y
