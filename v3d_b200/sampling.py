@@ -39,7 +39,7 @@ class EDMDiscretization:
 
     def get_sigmas(self, n: int, device="cpu") -> torch.Tensor:
         # computed on the host in fp32 exactly like the reference's torch.linspace expression
-        ramp = torch.linspace(0, 1, n)
+        ramp = torch.linspace(0, 1, n, device="cpu")
         min_inv_rho = self.sigma_min ** (1 / self.rho)
         max_inv_rho = self.sigma_max ** (1 / self.rho)
         return ((max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** self.rho).to(device)
@@ -57,7 +57,7 @@ class LinearPredictionGuider:
     def __init__(self, max_scale: float, num_frames: int, min_scale: float = 1.0,
                  additional_cond_keys: Optional[Union[List[str], str]] = None):
         self.min_scale, self.max_scale, self.num_frames = min_scale, max_scale, num_frames
-        self.scale = torch.linspace(min_scale, max_scale, num_frames).unsqueeze(0)
+        self.scale = torch.linspace(min_scale, max_scale, num_frames, device="cpu").unsqueeze(0)
         if additional_cond_keys is None:
             additional_cond_keys = []
         if isinstance(additional_cond_keys, str):
