@@ -119,7 +119,7 @@ class CpuReference:
     latent_d x latent_d latent, fp32, all host threads; extrapolated to the full workload by pixel count
     (the attention N^2 term is under-counted by this scaling, which favours the CPU number)."""
 
-    def __init__(self, T: int, S: int, latent: int, latent_u: int = 32, latent_d: int = 16):
+    def __init__(self, T: int, S: int, latent: int, latent_u: int = 16, latent_d: int = 8):
         import torch
         from oracle import ref_decoder, ref_unet  # the one place bench.py executes oracle/: the timed baseline
 
@@ -307,22 +307,35 @@ def run_native(args) -> None:
     step_e2e()  # warm the e2e-only pieces (pinned copies)
     secs_e2e, _, _ = timed(step_e2e, args.steps)
 
-    # ---- roofline of the dominant kernel family: instrument every tensor-core GEMM/conv launch of ONE step
-    records = []
-    orig_gemm = ops.gemm
+    # ---- roofline of the dominant kernel family + per-family breakdown: every launch of ONE step is bracketed
+    #      by CUDA events on the launching stream (a separate pass, so the timed region above carries no probes)
+    records = []      # (flops, e0, e1) for tensor-core GEMM/conv launches
+    families = {}     # op name -> list of (e0, e1)
+    host_only = {"launch_count", "pick_block_n", "geglu_perm"}
+    saved = {}
 
-    def probed(a, w, out, **kw):
-        K, N = kw["K"], kw["N"]
-        rows = kw["rows_per_batch"] * kw.get("batch", 1)
-        taps = 9 if kw.get("conv") is not None else kw.get("ntaps", 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig_gemm(a, w, out, **kw)
-        e1.record()
-        records.append((2.0 * rows * N * K * taps, e0, e1))
-        return r
+    def make_probe(name, fn):
+        def probed(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            fam = name
+            if name == "gemm":
+                K, N = kw["K"], kw["N"]
+                rows = kw["rows_per_batch"] * kw.get("batch", 1)
+                taps = 9 if kw.get("conv") is not None else kw.get("ntaps", 1)
+                records.append((2.0 * rows * N * K * taps, e0, e1))
+                fam = "gemm.conv3x3" if kw.get("conv") is not None else ("gemm.temporal" if taps == 3 else "gemm.linear")
+            families.setdefault(fam, []).append((e0, e1))
+            return r
+        return probed
 
-    ops.gemm = probed
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if callable(fn) and not name.startswith("_") and name not in host_only and getattr(fn, "__module__", "") == ops.__name__:
+            saved[name] = fn
+            setattr(ops, name, make_probe(name, fn))
     try:
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -331,10 +344,15 @@ def run_native(args) -> None:
         pe1.record()
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig_gemm
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
     gemm_flops = sum(r[0] for r in records)
     gemm_ms = sum(r[1].elapsed_time(r[2]) for r in records)
     probe_ms = pe0.elapsed_time(pe1)
+    breakdown = {k: {"ms": round(sum(a.elapsed_time(b) for a, b in v), 3), "launches": len(v)}
+                 for k, v in sorted(families.items())}
+    breakdown["_probed_step_ms"] = round(probe_ms, 3)
+    breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
 
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
@@ -359,6 +377,7 @@ def run_native(args) -> None:
             "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
             "launches_per_step": len(records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
+            "breakdown_ms_per_step": breakdown,
             "model": {"reference_accounting_tflop_per_step": model_tf,
                       "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
         },
