@@ -118,9 +118,13 @@ int v3d_softmax_rows_f32(const void* x, void* y, int64_t rows, int32_t n, float 
  * (row stride ld_qkv elements); heads are 64-column groups.
  * ------------------------------------------------------------------------------------------ */
 /* F.scaled_dot_product_attention / xformers FMHA, attention.py:337-341,432-444: per (sample, head)
- * softmax(q k^T scale) v over ntok tokens; token rows are sample-major. */
+ * softmax(q k^T scale) v over ntok tokens; token rows are sample-major. tcgen05 MMAs (S = QK^T and O = PV with
+ * TMEM accumulators), TMA-staged Q/K/V tiles, warp-specialised fp32 softmax. */
 int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
                           int32_t nbatch, int32_t ntok, int32_t nheads, float scale, void* stream);
+/* validation twin of v3d_attention_spatial on mma.sync (same contract); not used by the product path. */
+int v3d_attention_spatial_mma(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
+                              int32_t nbatch, int32_t ntok, int32_t nheads, float scale, void* stream);
 /* the same attention across the T view-frames of each pixel (video_attention.py:114,125), reading the
  * frame-major token matrix in place: row(b,t,s) = (b*T + t)*S + s, T <= 32. */
 int v3d_attention_temporal(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,

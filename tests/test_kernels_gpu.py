@@ -232,11 +232,13 @@ def test_softmax_rows():
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nb,ntok,heads", [(2, 16, 4), (3, 64, 20), (2, 256, 10), (2, 1024, 5), (1, 4096, 5),
                                            (2, 200, 2), (1, 1000, 3)])
-def test_attention_spatial(nb, ntok, heads):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+def test_attention_spatial(nb, ntok, heads, impl):
     c = heads * 64
     qkv = rnd(nb * ntok, 3 * c)
     out = torch.empty(nb * ntok, c, device=DEV, dtype=torch.bfloat16)
-    ops.attention_spatial(qkv, out, nb, ntok, heads, 64 ** -0.5)
+    fn = ops.attention_spatial if impl == "tcgen05" else ops.attention_spatial_mma
+    fn(qkv, out, nb, ntok, heads, 64 ** -0.5)
     q, k, v = [t.reshape(nb, ntok, heads, 64).permute(0, 2, 1, 3).float() for t in qkv.split(c, dim=-1)]
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(nb * ntok, c)
     assert_close(out, ref, atol=3e-2, what="spatial attention")

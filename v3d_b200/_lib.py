@@ -52,6 +52,7 @@ SIGNATURES = {
     "v3d_softmax_rows_f32": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),
     # attention.cu
     "v3d_attention_spatial": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
+    "v3d_attention_spatial_mma": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "v3d_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
     # elementwise.cu
     "v3d_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

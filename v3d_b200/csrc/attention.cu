@@ -1,7 +1,8 @@
 // Attention kernels, head dim 64, bf16 in / fp32 softmax / bf16 out.
 //   spatial : flash attention over N tokens per (sample, head); streaming K/V tiles through shared
 //             memory with cp.async double buffering, online softmax in registers.
-//             (bring-up path on mma.sync m16n8k16; the tcgen05 S/P/O-in-TMEM variant replaces it)
+//             (mma.sync m16n8k16 bring-up kernel, exported as v3d_attention_spatial_mma for cross-checks;
+//             the product kernel is the tcgen05 one in attention_tc.cu)
 //   temporal: sequences of T <= 32 view-frames per (pixel, head); one warp per sequence, whole
 //             problem on chip, no online softmax. Reads q/k/v with the frame stride directly from the
 //             frame-major token matrix, so "(b t) s c -> (b s) t c" is never materialised.
@@ -347,14 +348,16 @@ using namespace v3d;
 
 extern "C" {
 
-/* softmax(q k^T * scale) v per (sample, head), head dim 64; q/k/v are column slices of one packed
+/* Bring-up / cross-check implementation of v3d_attention_spatial on mma.sync (kept for validation of the
+ * tcgen05 kernel in tests; the product path calls v3d_attention_spatial).
+ * softmax(q k^T * scale) v per (sample, head), head dim 64; q/k/v are column slices of one packed
  * projection matrix (row stride ld_qkv), token rows sample-major. Replaces
  * F.scaled_dot_product_attention / xformers FMHA at sgm/modules/attention.py:337-341,432-444. */
-int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
+int v3d_attention_spatial_mma(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
                           int32_t nbatch, int32_t ntok, int32_t nheads, float scale, void* stream) {
   if (!q || !k || !v || !o || ld_qkv % 8 != 0 || ld_o % 8 != 0 || nbatch <= 0 || ntok <= 0 || nheads <= 0 ||
       nheads > 65535 || nbatch > 65535) {
-    set_error("v3d_attention_spatial: bad args");
+    set_error("v3d_attention_spatial_mma: bad args");
     return V3D_ERR_BAD_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -109,57 +109,83 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 }
 
 // ---------------- small-M linear: y[m,n] (+)= act_out( sum_k act_in(x[m,k]) W[n,k] + b[n] ) ----------------
-// x fp32 [M,K] (M <= 64), W bf16 [N,K], y fp32 [M,N]. One warp per output column; lanes stride over K
-// with 16-byte weight loads; x is re-read through L1 (it is tiny and shared by every warp).
+// x fp32 [M,K] (M <= 64), W bf16 [N,K], y fp32 [M,N].  A CTA of 8 warps owns 32 output columns (4 per warp).
+// x is staged once per K-chunk in shared memory with act_in already applied (so SiLU is evaluated once per CTA,
+// not once per output column); each lane streams 16-byte weight vectors and FMAs them against smem rows.
 constexpr int kSlMaxM = 64;
-constexpr int kSlChunk = 8;  // rows of x processed per pass over the weight row
+constexpr int kSlCols = 4;     // output columns per warp
+constexpr int kSlKc = 256;     // K-chunk staged in smem (one 8-element vector per lane)
+constexpr int kSlMc = 16;      // rows of x accumulated per pass
 
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ y, int M, int K, int N, int act_in, int act_out, int accumulate,
                     long long ldx, long long ldy) {
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
-  const bf16* wr = W + static_cast<long long>(n) * K;
-  const float bv = bias ? bias[n] : 0.f;
-  for (int m0 = 0; m0 < M; m0 += kSlChunk) {
-    float acc[kSlChunk];
+  __shared__ __align__(16) float sx[kSlMc][kSlKc + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 8 + warp) * kSlCols;
+  // per-lane partial sums live in registers per pass; final sums are reduced across lanes
+  for (int m0 = 0; m0 < M; m0 += kSlMc) {
+    float part[kSlCols][kSlMc];
 #pragma unroll
-    for (int i = 0; i < kSlChunk; ++i) acc[i] = 0.f;
-    for (int k = lane * 8; k < K; k += 256) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
-      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
-      float w[8];
+    for (int cidx = 0; cidx < kSlCols; ++cidx)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(wv[j]);
-        w[2 * j] = f.x;
-        w[2 * j + 1] = f.y;
+      for (int i = 0; i < kSlMc; ++i) part[cidx][i] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += kSlKc) {
+      __syncthreads();
+      // stage x[m0..m0+Mc)[k0..k0+Kc) with act_in applied
+      for (int i = threadIdx.x; i < kSlMc * (kSlKc / 4); i += blockDim.x) {
+        const int r = i / (kSlKc / 4), c4 = (i % (kSlKc / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < M && k0 + c4 < K) v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + r) * ldx + k0 + c4));
+        if (act_in == V3D_ACT_SILU) {
+          v.x = v.x / (1.0f + expf(-v.x)); v.y = v.y / (1.0f + expf(-v.y));
+          v.z = v.z / (1.0f + expf(-v.z)); v.w = v.w / (1.0f + expf(-v.w));
+        }
+        *reinterpret_cast<float4*>(&sx[r][c4]) = v;
       }
+      __syncthreads();
+      const int k = k0 + lane * 8;
+      if (k < K) {
+        float w[kSlCols][8];
 #pragma unroll
-      for (int i = 0; i < kSlChunk; ++i) {
-        if (m0 + i < M) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * ldx + k));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + i) * ldx + k + 4));
-          float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          if (act_in == V3D_ACT_SILU) {
+        for (int cidx = 0; cidx < kSlCols; ++cidx) {
+          const int n = n0 + cidx;
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (n < N) u = __ldg(reinterpret_cast<const uint4*>(W + static_cast<long long>(n) * K + k));
+          const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = xv[j] / (1.0f + expf(-xv[j]));
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(wv[j]);
+            w[cidx][2 * j] = f.x;
+            w[cidx][2 * j + 1] = f.y;
           }
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i] = fmaf(xv[j], w[j], acc[i]);
+        for (int i = 0; i < kSlMc; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(&sx[i][lane * 8]);
+          const float4 b = *reinterpret_cast<const float4*>(&sx[i][lane * 8 + 4]);
+          const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int cidx = 0; cidx < kSlCols; ++cidx)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[cidx][i] = fmaf(xv[j], w[cidx][j], part[cidx][i]);
         }
       }
     }
 #pragma unroll
-    for (int i = 0; i < kSlChunk; ++i) {
-      const float s = warp_sum(acc[i]);
-      if (lane == 0 && m0 + i < M) {
-        float v = s + bv;
-        if (act_out == V3D_ACT_SILU) v = v / (1.0f + expf(-v));
-        float* o = y + static_cast<long long>(m0 + i) * ldy + n;
-        *o = accumulate ? *o + v : v;
+    for (int cidx = 0; cidx < kSlCols; ++cidx) {
+      const int n = n0 + cidx;
+      const float bv = (bias != nullptr && n < N) ? bias[n] : 0.f;
+#pragma unroll
+      for (int i = 0; i < kSlMc; ++i) {
+        const float sres = warp_sum(part[cidx][i]);
+        if (lane == 0 && n < N && m0 + i < M) {
+          float v = sres + bv;
+          if (act_out == V3D_ACT_SILU) v = v / (1.0f + expf(-v));
+          float* o = y + static_cast<long long>(m0 + i) * ldy + n;
+          *o = accumulate ? *o + v : v;
+        }
       }
     }
   }
@@ -307,8 +333,8 @@ int v3d_small_linear(const void* x, const void* W, const void* bias, void* y, in
     set_error("v3d_small_linear: bad args M=%d K=%d N=%d", M, K, N);
     return V3D_ERR_BAD_ARG;
   }
-  const int warps = 8;
-  small_linear_kernel<<<(N + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int cols_per_cta = 8 * kSlCols;
+  small_linear_kernel<<<(N + cols_per_cta - 1) / cols_per_cta, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(x), static_cast<const bf16*>(W), static_cast<const float*>(bias),
       static_cast<float*>(y), M, K, N, act_in, act_out, accumulate, ldx, ldy);
   V3D_CHECK_LAUNCH("small_linear_kernel");

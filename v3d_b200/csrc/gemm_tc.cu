@@ -3,7 +3,7 @@
 // One persistent, warp-specialised kernel:
 //   warp 0      : TMA producer  (A tile 128x64 bf16 + B tile BNx64 bf16 per pipeline stage, 128B swizzle)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> bias / per-frame bias / SiLU / GEGLU / residual blend ->
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> bias / per-frame bias / SiLU / GEGLU / residual blend ->
 //                 bf16 or fp32 stores). Two TMEM accumulator stages so the epilogue of tile i overlaps
 //                 the main loop of tile i+1.
 // Operand gather modes (see include/v3d_b200.h): linear rows, 3-tap temporal shift, 3x3 spatial taps.
@@ -17,7 +17,7 @@ namespace v3d {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kSmemBudget = 225 * 1024;
 
 struct GemmEpi {
@@ -75,7 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -172,11 +172,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
+    // Two warps per TMEM lane quarter; each takes half of the tile's 16-column chunks. Residual operands of
+    // the next chunk are prefetched before the current chunk's TMEM load is consumed, so the global-load
+    // latency is off the per-chunk critical path.
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
     const bool geglu = p.act == V3D_ACT_GEGLU;
     const int out_cols = geglu ? BN / 2 : BN;
+    const int nchunks = out_cols / 16;
+    const int c_begin = half ? (nchunks + 1) / 2 : 0;
+    const int c_end = half ? nchunks : (nchunks + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -201,19 +208,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         row = static_cast<long long>(b) * p.rows_per_batch + m;
       }
       const float* fb = nullptr;
-      if (p.fbias != nullptr && valid)
-        fb = p.fbias + (row / p.rows_per_frame) * p.ldfb;
+      if (p.fbias != nullptr && valid) fb = p.fbias + (row / p.rows_per_frame) * p.ldfb;
+      const int obase = n_tile * out_cols;  // first output column of this tile
+      const bf16* r1p = (p.R1 != nullptr && valid) ? p.R1 + row * p.ldr1 + obase : nullptr;
+      const bf16* r2p = (p.R2 != nullptr && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
+
+      uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;  // residuals of the current chunk
+      if (c_begin < c_end) {
+        if (r1p) { ra0 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16)); ra1 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16) + 1); }
+        if (r2p) { rb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); rb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc =
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int c = 0; c < out_cols; c += 16) {
+#pragma unroll 1
+      for (int ci = c_begin; ci < c_end; ++ci) {
+        const int c = ci * 16;
         uint32_t v[16];
         uint32_t g[16];
         tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
         if (geglu) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
+        // prefetch the next chunk's residuals while the TMEM load is in flight
+        uint4 na0 = ra0, na1 = ra1, nb0 = rb0, nb1 = rb1;
+        if (ci + 1 < c_end) {
+          if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16) + 1); }
+          if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16) + 1); }
+        }
         tmem_ld_wait();
         if (valid) {
           float f[16];
@@ -223,14 +246,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + ncol + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + j));
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
           if (fb != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(fb + ncol + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(fb + ncol + j));
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
@@ -241,23 +264,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (p.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + ncol + BN / 2 + j);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + BN / 2 + j));
                 gt[j] += b4.x; gt[j + 1] += b4.y; gt[j + 2] += b4.z; gt[j + 3] += b4.w;
               }
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_f(gt[j]);
+            for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_fast(gt[j]);
           } else if (p.act == V3D_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
           }
-          const int ocol = n_tile * out_cols + c;  // column in the output
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-          if (p.R1 != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.R1 + row * p.ldr1 + ocol);
-            const uint4 a = rp[0], b = rp[1];
-            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (r1p) {
+            const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float2 t = unpack_bf16x2(u[j]);
@@ -265,10 +285,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               f[2 * j + 1] += p.s1 * t.y;
             }
           }
-          if (p.R2 != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.R2 + row * p.ldr2 + ocol);
-            const uint4 a = rp[0], b = rp[1];
-            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (r2p) {
+            const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float2 t = unpack_bf16x2(u[j]);
@@ -276,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               f[2 * j + 1] += p.s2 * t.y;
             }
           }
+          const int ocol = obase + c;
           if (p.out_fp32) {
             float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + ocol);
 #pragma unroll
@@ -289,6 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
           }
         }
+        ra0 = na0; ra1 = na1; rb0 = nb0; rb1 = nb1;
       }
       tc_fence_before();
       __syncwarp();

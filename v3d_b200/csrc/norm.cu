@@ -12,6 +12,7 @@ namespace v3d {
 // grid = (row chunks, samples); each thread owns one 8-channel vector column and strides over rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
+constexpr int kGnUnroll = 4;  // independent 16-byte loads in flight per thread
 
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, long long rows_per_sample,
@@ -25,29 +26,44 @@ gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, long lon
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
 
-  const int lanes_r = blockDim.x / vpr;  // row lanes (>=1 guaranteed by host)
+  const int lanes_r = blockDim.x / vpr;  // row lanes (block = vpr * lanes_r threads)
   const int vc = threadIdx.x % vpr;
   const int rl = threadIdx.x / vpr;
-  if (rl < lanes_r) {
-    float s[8], q[8];
+  float s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    const bf16* base = x + (static_cast<long long>(sample) * rows_per_sample) * ldx + vc * 8;
-    for (long long r = row0 + rl; r < row1; r += lanes_r) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * ldx));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const bf16* base = x + (static_cast<long long>(sample) * rows_per_sample) * ldx + vc * 8;
+  long long r = row0 + rl;
+  for (; r + static_cast<long long>(kGnUnroll - 1) * lanes_r < row1; r += static_cast<long long>(kGnUnroll) * lanes_r) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k)
+      u[k] = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(k) * lanes_r) * ldx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16x2(w[j]);
-        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+        s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+        s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
       }
     }
+  }
+  for (; r < row1; r += lanes_r) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + r * ldx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[vc * 8 + j], s[j]);
-      atomicAdd(&s_acc[C + vc * 8 + j], q[j]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+      s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[vc * 8 + j], s[j]);
+    atomicAdd(&s_acc[C + vc * 8 + j], q[j]);
   }
   __syncthreads();
   const int cg = C / groups;
@@ -63,55 +79,75 @@ gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, long lon
   }
 }
 
-// y = act((x - mean) * rstd * gamma + beta); per-sample per-channel scale/shift precomputed in smem.
-__global__ void __launch_bounds__(kGnThreads)
+// y = act((x - mean) * rstd * gamma + beta). Each thread owns one 8-channel vector column: its scale/shift
+// (16 floats) are computed once from the statistics and kept in registers; no smem, no div/mod in the loop.
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 long long rows_per_sample, int C, long long ldx, int groups, float eps, int silu,
                 int rows_per_cta) {
-  extern __shared__ float s_ab[];  // [2][C]: scale, shift
+  const int vpr = C >> 3;
   const int sample = blockIdx.y;
+  const int lanes_r = blockDim.x / vpr;
+  const int vc = threadIdx.x % vpr;
+  const int rl = threadIdx.x / vpr;
   const int cg = C / groups;
   const double cnt = static_cast<double>(rows_per_sample) * cg;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cg;
-    const double* st = stats + (static_cast<long long>(sample) * groups + g) * 2;
-    const double mean = st[0] / cnt;
-    double var = st[1] / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float a = rstd * gamma[c];
-    s_ab[c] = a;
-    s_ab[C + c] = beta[c] - static_cast<float>(mean) * a;
+  float sc[8], sh[8];
+  {
+    int g_prev = -1;
+    float mean_f = 0.f, rstd_f = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      const int g = c / cg;
+      if (g != g_prev) {
+        const double* st = stats + (static_cast<long long>(sample) * groups + g) * 2;
+        const double mean = st[0] / cnt;
+        double var = st[1] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mean_f = static_cast<float>(mean);
+        rstd_f = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        g_prev = g;
+      }
+      const float a = rstd_f * __ldg(gamma + c);
+      sc[j] = a;
+      sh[j] = __ldg(beta + c) - mean_f * a;
+    }
   }
-  __syncthreads();
-  const int vpr = C >> 3;
   const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   long long row1 = row0 + rows_per_cta;
   if (row1 > rows_per_sample) row1 = rows_per_sample;
-  const long long nvec = (row1 - row0) * vpr;
   const long long srow = static_cast<long long>(sample) * rows_per_sample;
-  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const long long r = row0 + i / vpr;
-    const int vc = static_cast<int>(i % vpr);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (srow + r) * ldx + vc * 8));
+  const bf16* xb = x + srow * ldx + vc * 8;
+  bf16* yb = y + srow * static_cast<long long>(C) + vc * 8;
+
+  auto emit = [&](const uint4& u, long long r) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(w[j]);
-      const int c = vc * 8 + 2 * j;
-      float a = f.x * s_ab[c] + s_ab[C + c];
-      float b = f.y * s_ab[c + 1] + s_ab[C + c + 1];
+      float a = fmaf(f.x, sc[2 * j], sh[2 * j]);
+      float b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
       if (silu) {
         a = silu_f(a);
         b = silu_f(b);
       }
       o[j] = pack_bf16x2(a, b);
     }
-    *reinterpret_cast<uint4*>(y + (srow + r) * static_cast<long long>(C) + vc * 8) =
-        make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(yb + r * static_cast<long long>(C)) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  long long r = row0 + rl;
+  for (; r + static_cast<long long>(kGnUnroll - 1) * lanes_r < row1; r += static_cast<long long>(kGnUnroll) * lanes_r) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k)
+      u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (r + static_cast<long long>(k) * lanes_r) * ldx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) emit(u[k], r + static_cast<long long>(k) * lanes_r);
   }
+  for (; r < row1; r += lanes_r) emit(__ldg(reinterpret_cast<const uint4*>(xb + r * ldx)), r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,6 +158,7 @@ gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const double* 
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // 8 vectors * 8 elements * 32 lanes = 2048 channels
 
+template <int VPL>  // 16-byte vectors per lane: C <= VPL * 256
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16* __restrict__ ysum,
                  bf16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -131,12 +168,12 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16
   const int vpr = C >> 3;
   for (long long row = static_cast<long long>(blockIdx.x) * warps + (threadIdx.x >> 5); row < rows;
        row += static_cast<long long>(gridDim.x) * warps) {
-    float v[kLnMaxVec][8];
+    float v[VPL][8];
     const bf16* xr = x + row * C;
     const float* ar = add ? add + (row / rows_per_frame) * C : nullptr;
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int vc = lane + i * 32;
       if (vc < vpr) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vc * 8));
@@ -169,7 +206,7 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16
     const float mean = s / static_cast<float>(C);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       if (lane + i * 32 < vpr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -181,7 +218,7 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16
     q = warp_sum(q);
     const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int vc = lane + i * 32;
       if (vc < vpr) {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vc * 8));
@@ -314,8 +351,8 @@ softmax_rows_f32_kernel(const float* __restrict__ x, bf16* __restrict__ y, int n
 }
 
 static int pick_rows_per_cta(long long rows_per_sample, int nsamples) {
-  // aim for >= ~4 waves of CTAs over the SMs while keeping at least 32 rows per CTA
-  const long long target = 4LL * num_sms();
+  // aim for >= ~8 waves of CTAs over the SMs while keeping at least 32 rows per CTA
+  const long long target = 8LL * num_sms();
   long long chunks = (target + nsamples - 1) / nsamples;
   if (chunks < 1) chunks = 1;
   long long rpc = (rows_per_sample + chunks - 1) / chunks;
@@ -367,9 +404,15 @@ int v3d_groupnorm_apply(const void* x, void* y, const void* stats, const void* g
     return V3D_ERR_BAD_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C / 8 > 512) {
+    set_error("v3d_groupnorm_apply: C=%d too wide", C);
+    return V3D_ERR_BAD_ARG;
+  }
   const int rpc = pick_rows_per_cta(rows_per_sample, nsamples);
   dim3 grid(static_cast<unsigned>((rows_per_sample + rpc - 1) / rpc), nsamples);
-  gn_apply_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), st>>>(
+  const int vpr = C / 8;
+  const int lanes_r = kGnThreads / vpr > 0 ? kGnThreads / vpr : 1;
+  gn_apply_kernel<<<grid, vpr * lanes_r, 0, st>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(y), static_cast<const double*>(stats),
       static_cast<const float*>(gamma), static_cast<const float*>(beta), rows_per_sample, C, ldx, groups,
       eps, silu, rpc);
@@ -388,12 +431,23 @@ int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const voi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int warps = 8;
   long long blocks = (rows + warps - 1) / warps;
-  const long long cap = 16LL * num_sms();
+  const long long cap = 32LL * num_sms();
   if (blocks > cap) blocks = cap;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(
-      static_cast<const bf16*>(x), static_cast<const float*>(add), static_cast<bf16*>(ysum),
-      static_cast<bf16*>(y), static_cast<const float*>(gamma), static_cast<const float*>(beta), rows, C,
-      rows_per_frame > 0 ? rows_per_frame : 1, eps);
+  const int vpl = (C / 8 + 31) / 32;
+#define V3D_LN_LAUNCH(V)                                                                                   \
+  layernorm_kernel<V><<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(                                \
+      static_cast<const bf16*>(x), static_cast<const float*>(add), static_cast<bf16*>(ysum),               \
+      static_cast<bf16*>(y), static_cast<const float*>(gamma), static_cast<const float*>(beta), rows, C,   \
+      rows_per_frame > 0 ? rows_per_frame : 1, eps)
+  switch (vpl) {
+    case 1: V3D_LN_LAUNCH(1); break;
+    case 2: V3D_LN_LAUNCH(2); break;
+    case 3: V3D_LN_LAUNCH(3); break;
+    case 4: V3D_LN_LAUNCH(4); break;
+    case 5: V3D_LN_LAUNCH(5); break;
+    default: V3D_LN_LAUNCH(8); break;
+  }
+#undef V3D_LN_LAUNCH
   V3D_CHECK_LAUNCH("layernorm_kernel");
   return V3D_OK;
 }

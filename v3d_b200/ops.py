@@ -156,6 +156,19 @@ def attention_spatial(qkv: torch.Tensor, out: torch.Tensor, nbatch: int, ntok: i
     return out
 
 
+def attention_spatial_mma(qkv: torch.Tensor, out: torch.Tensor, nbatch: int, ntok: int, nheads: int,
+                          scale: float) -> torch.Tensor:
+    """Validation twin of attention_spatial (mma.sync kernel); tests only."""
+    _need(qkv, torch.bfloat16, "attention qkv")
+    c = nheads * 64
+    es = qkv.element_size()
+    base = qkv.data_ptr()
+    _lib.check(_lib.load().v3d_attention_spatial_mma(base, base + c * es, base + 2 * c * es, out.data_ptr(),
+                                                     qkv.shape[-1], out.shape[-1], nbatch, ntok, nheads, scale,
+                                                     _stream()), "v3d_attention_spatial_mma")
+    return out
+
+
 def attention_temporal(qkv: torch.Tensor, out: torch.Tensor, nb: int, t: int, s: int, nheads: int,
                        scale: float) -> torch.Tensor:
     _need(qkv, torch.bfloat16, "attention qkv")
