@@ -77,6 +77,9 @@ typedef struct v3d_gemm_args {
   int32_t out_fp32;
   int32_t conv_n, conv_h, conv_w; /* conv3x3 mode when conv_w > 0 (then batch/rows_per_batch ignored) */
   int32_t block_n;                /* 0 = auto; else force the N tile (16,32,64,128,160,256) */
+  /* small-M mode (the M<=64 embedding linears run as W[N_w,K] x X[64,K]^T): D is fp32 [valid_cols][ldd] written
+   * transposed (D[col][row] = acc + bias[row]), optionally accumulated into; columns >= valid_cols are dropped */
+  int32_t out_transposed, valid_cols, accumulate;
   float s0, s1, s2;
 } v3d_gemm_args;
 
@@ -153,6 +156,8 @@ int v3d_nhwc_to_nchw_f32(const void* x, void* y, int32_t N, int32_t C, int32_t H
  * (video_attention.py:220-224,275), single-token cross-attention to_out(to_v(ctx)) (attention.py:277-283). */
 int v3d_small_linear(const void* x, const void* W, const void* bias, void* y, int32_t M, int32_t K, int32_t N,
                      int32_t act_in, int32_t act_out, int32_t accumulate, int64_t ldx, int64_t ldy, void* stream);
+/* operand prep for the tensor-core small-M path: y bf16 [64][K] = act_in(x fp32 [M][ldx]), rows >= M zero. */
+int v3d_prep_small_x(const void* x, int64_t ldx, void* y, int32_t M, int32_t K, int32_t act_in, void* stream);
 /* timestep_embedding (diffusionmodules/util.py:207-231): out[n][dim] = cos | sin, fp32. */
 int v3d_timestep_embedding(const void* t, void* out, int32_t n, int32_t dim, float max_period, void* stream);
 int v3d_add_rows(const void* a, const void* b, void* out, int32_t rows, int32_t cols, void* stream);

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("rows_per_frame", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
         ("conv_n", C.c_int32), ("conv_h", C.c_int32), ("conv_w", C.c_int32),
         ("block_n", C.c_int32),
+        ("out_transposed", C.c_int32), ("valid_cols", C.c_int32), ("accumulate", C.c_int32),
         ("s0", C.c_float), ("s1", C.c_float), ("s2", C.c_float),
     ]
 
@@ -61,6 +62,7 @@ SIGNATURES = {
     "v3d_nchw_f32_to_nhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "v3d_nhwc_to_nchw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp]),
     "v3d_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp]),
+    "v3d_prep_small_x": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp]),
     "v3d_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "v3d_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "v3d_time_mix_conv": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),

@@ -209,6 +209,21 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
   }
 }
 
+// ---------------- operand prep for the small-M tensor-core path: y[64][K] bf16 = act_in(x[M][ldx]) (rows >= M zero)
+__global__ void prep_small_x_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y, int M, int K,
+                                    int act_in) {
+  const int total = 64 * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / K, c = i - r * K;
+    float v = 0.f;
+    if (r < M) {
+      v = x[static_cast<long long>(r) * ldx + c];
+      if (act_in == V3D_ACT_SILU) v = v / (1.0f + expf(-v));
+    }
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
                                 long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -368,6 +383,19 @@ int v3d_time_mix_conv(const void* x, int64_t ldx, const void* w, const void* bia
                                                               static_cast<const float*>(bias),
                                                               static_cast<float*>(y), nb, T, HW, C);
   V3D_CHECK_LAUNCH("time_mix_conv_kernel");
+  return V3D_OK;
+}
+
+/* Operand prep for running an M<=64 linear on the tensor cores as W[N,K] x X[64,K]^T (v3d_gemm_bf16 with
+ * out_transposed): y bf16 [64][K] = act_in(x fp32 [M][ldx]), rows M..63 zero. */
+int v3d_prep_small_x(const void* x, int64_t ldx, void* y, int32_t M, int32_t K, int32_t act_in, void* stream) {
+  if (!x || !y || M <= 0 || M > 64 || K <= 0) {
+    set_error("v3d_prep_small_x: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  prep_small_x_kernel<<<blocks_for(64LL * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), ldx > 0 ? ldx : K, static_cast<bf16*>(y), M, K, act_in);
+  V3D_CHECK_LAUNCH("prep_small_x_kernel");
   return V3D_OK;
 }
 

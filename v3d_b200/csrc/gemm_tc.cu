@@ -31,6 +31,7 @@ struct GemmEpi {
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
   int rows_per_frame, act, out_fp32;
   int b_batched;
+  int transposed, valid_cols, accumulate;  // small-M mode: D is fp32 [cols][ldd], D[col][row]; bias per row
   // conv3x3 geometry
   int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h;
   int num_m_tiles, num_n_tiles;
@@ -42,11 +43,12 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE_RAW = (kSmemBudget - 2048) / STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 8 * 4096;  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled
+  static constexpr int NSTAGE_RAW = (kSmemBudget - 2048 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool CONV>
@@ -57,7 +59,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::NSTAGE * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
   uint64_t* tfull_bar = empty_bar + C::NSTAGE;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -173,45 +176,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ------------------------------ epilogue (warps 2..9) ------------------------------
-    // Two warps per TMEM lane quarter; each takes half of the tile's 16-column chunks. Residual operands of
-    // the next chunk are prefetched before the current chunk's TMEM load is consumed, so the global-load
-    // latency is off the per-chunk critical path.
+    // Two warps per TMEM lane quarter; each takes half of the tile's 16-column chunks.  bf16 results go through a
+    // per-warp swizzled smem slab (32 rows x 128 B) and leave as row-contiguous 16-byte stores (4 full 128-byte
+    // lines per warp instruction instead of 32 half-sectors).  Residual operands of the next chunk are
+    // prefetched while the current chunk's TMEM load is in flight.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
+    uint8_t* stg = staging + (warp - 2) * 4096;
     const bool geglu = p.act == V3D_ACT_GEGLU;
     const int out_cols = geglu ? BN / 2 : BN;
     const int nchunks = out_cols / 16;
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
+    const bool staged = !p.out_fp32 && !p.transposed;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
-      long long row;
-      bool valid;
+      // tile row -> (valid, global row); also used for other lanes' rows in the coalesced copy-out
+      int t0 = 0, t1 = 0, t2 = 0;
       if (CONV) {
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        const int w = r % p.bw;
-        const int h = (r / p.bw) % p.bh;
-        const int n = r / (p.bw * p.bh);
-        const int img = tn * p.bn + n;
-        valid = img < p.cn;
-        row = (static_cast<long long>(img) * p.ch + (th * p.bh + h)) * p.cw + (tw * p.bw + w);
+        t0 = (m_tile % p.tiles_w) * p.bw;
+        t1 = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
+        t2 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
       } else {
-        const int b = m_tile / p.tiles_per_batch;
-        const int m = (m_tile % p.tiles_per_batch) * BM + r;
-        valid = m < p.rows_per_batch;
-        row = static_cast<long long>(b) * p.rows_per_batch + m;
+        t0 = m_tile / p.tiles_per_batch;
+        t1 = (m_tile % p.tiles_per_batch) * BM;
       }
+      auto map_row = [&](int tr, long long& grow) -> bool {
+        if (CONV) {
+          const int w = tr % p.bw;
+          const int h = (tr / p.bw) % p.bh;
+          const int img = t2 + tr / (p.bw * p.bh);
+          grow = (static_cast<long long>(img) * p.ch + (t1 + h)) * p.cw + (t0 + w);
+          return img < p.cn;
+        } else {
+          const int m = t1 + tr;
+          grow = static_cast<long long>(t0) * p.rows_per_batch + m;
+          return m < p.rows_per_batch;
+        }
+      };
+      long long row;
+      const bool valid = map_row(r, row);
       const float* fb = nullptr;
       if (p.fbias != nullptr && valid) fb = p.fbias + (row / p.rows_per_frame) * p.ldfb;
       const int obase = n_tile * out_cols;  // first output column of this tile
       const bf16* r1p = (p.R1 != nullptr && valid) ? p.R1 + row * p.ldr1 + obase : nullptr;
       const bf16* r2p = (p.R2 != nullptr && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
+      const float row_bias = (p.transposed && p.bias != nullptr && valid) ? __ldg(p.bias + row) : 0.f;
 
       uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;  // residuals of the current chunk
       if (c_begin < c_end) {
@@ -224,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t t_acc =
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
+      int grp_first = c_begin;  // first chunk of the group currently being staged
 #pragma unroll 1
       for (int ci = c_begin; ci < c_end; ++ci) {
         const int c = ci * 16;
@@ -238,12 +253,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16) + 1); }
         }
         tmem_ld_wait();
-        if (valid) {
-          float f[16];
-          const int ncol = n_tile * BN + c;  // column in the (packed) N space
+        float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (valid) {
+          const int ncol = n_tile * BN + c;  // column in the (packed) N space
+          if (p.transposed) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += row_bias;
+          } else if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + j));
@@ -295,17 +313,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
           const int ocol = obase + c;
-          if (p.out_fp32) {
+          if (p.transposed) {
+            // D[col][row]: lanes hold consecutive rows -> each store instruction is one contiguous 128-byte line
+            float* dp = static_cast<float*>(p.D) + row;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (ocol + j < p.valid_cols) {
+                float* o = dp + static_cast<long long>(ocol + j) * p.ldd;
+                *o = p.accumulate ? *o + f[j] : f[j];
+              }
+            }
+          } else if (p.out_fp32) {
             float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + ocol);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* dp = reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + row * p.ldd + ocol);
-            dp[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            dp[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                               pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          }
+        }
+        if (staged) {
+          // stage this chunk (2 x 16 B) into the warp's slab at 16-byte slots (2k, 2k+1) of row `lane`
+          const int k = ci - grp_first;
+          uint8_t* srow = stg + lane * 128;
+          const int sw = lane & 7;
+          *reinterpret_cast<uint4*>(srow + (((2 * k) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          *reinterpret_cast<uint4*>(srow + (((2 * k + 1) ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          if (k == 3 || ci + 1 == c_end) {
+            // flush the group: (k+1) chunks = 2(k+1) 16-byte pieces per row, rows contiguous in global memory
+            __syncwarp();
+            const int ppr = 2 * (k + 1);
+            const int total = 32 * ppr;
+            const int gcol = obase + grp_first * 16;
+            for (int idx = lane; idx < total; idx += 32) {
+              const int rr = idx / ppr;
+              const int piece = idx - rr * ppr;
+              long long grow;
+              if (map_row(q * 32 + rr, grow)) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
+              }
+            }
+            __syncwarp();
+            grp_first = ci + 1;
           }
         }
         ra0 = na0; ra1 = na1; rb0 = nb0; rb1 = nb1;
@@ -408,6 +458,10 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     set_error("v3d_gemm_bf16: K=%d must be a multiple of 64 and N=%d of 16", a->K, a->N);
     return V3D_ERR_BAD_ARG;
   }
+  if (a->out_transposed && (conv || ntaps != 1 || !a->out_fp32 || a->batch > 1 || a->act == V3D_ACT_GEGLU || a->R1 || a->R2 || a->fbias)) {
+    set_error("v3d_gemm_bf16: out_transposed needs a plain fp32 linear GEMM (no taps/conv/batch/residual/geglu)");
+    return V3D_ERR_BAD_ARG;
+  }
   if (!conv && ntaps != 1 && ntaps != 3) {
     set_error("v3d_gemm_bf16: ntaps must be 1 or 3");
     return V3D_ERR_BAD_ARG;
@@ -441,6 +495,9 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   e.rows_per_frame = a->rows_per_frame > 0 ? a->rows_per_frame : 1;
   e.act = a->act;
   e.out_fp32 = a->out_fp32;
+  e.transposed = a->out_transposed;
+  e.valid_cols = a->valid_cols > 0 ? a->valid_cols : a->N;
+  e.accumulate = a->accumulate;
   e.s0 = a->s0;
   e.s1 = a->s1;
   e.s2 = a->s2;

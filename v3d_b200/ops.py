@@ -54,7 +54,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
          ldfb: int = 0,
          r1: Optional[torch.Tensor] = None, ldr1: int = 0, r2: Optional[torch.Tensor] = None, ldr2: int = 0,
          s0: float = 1.0, s1: float = 1.0, s2: float = 1.0, act: int = ACT_NONE, ntaps: int = 1,
-         tap_shift: int = 0, conv: Optional[tuple] = None, block_n: int = 0) -> torch.Tensor:
+         tap_shift: int = 0, conv: Optional[tuple] = None, block_n: int = 0, transposed: bool = False,
+         valid_cols: int = 0, accumulate: bool = False) -> torch.Tensor:
     """General entry to v3d_gemm_bf16. `conv=(n, h, w)` selects the implicit 3x3 conv gather."""
     _need(a, torch.bfloat16, "gemm A")
     _need(w, torch.bfloat16, "gemm B")
@@ -84,6 +85,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
     if conv is not None:
         g.conv_n, g.conv_h, g.conv_w = conv
     g.block_n = block_n
+    g.out_transposed = 1 if transposed else 0
+    g.valid_cols = valid_cols
+    g.accumulate = 1 if accumulate else 0
     g.s0, g.s1, g.s2 = s0, s1, s2
     _lib.check(_lib.load().v3d_gemm_bf16(C.byref(g), _stream()), "v3d_gemm_bf16")
     return out
@@ -217,8 +221,12 @@ def nhwc_to_nchw_f32(x: torch.Tensor, y: torch.Tensor, n: int, c: int, hw: int, 
 
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *,
                  act_in: int = ACT_NONE, act_out: int = ACT_NONE, accumulate: bool = False) -> torch.Tensor:
-    """y[M,N] fp32 = act_out(act_in(x) @ w.T + bias). x and y may be column slices of wider row-major
-    buffers (their row strides are taken from the tensors); M is processed in chunks of 64 rows."""
+    """y[M,N] fp32 (+)= act_out(act_in(x) @ w.T + bias) for the M<=64-row embedding linears. x and y may be column
+    slices of wider row-major buffers (row strides are taken from the tensors).
+
+    K % 64 == 0 and no output activation: tensor-core path — W is the 128-row operand streamed once by TMA,
+    act_in(x) is the 64-row operand, results are stored transposed (v3d_gemm_bf16 out_transposed).
+    Otherwise: the SIMT kernel v3d_small_linear."""
     _need(x, torch.float32, "small_linear x")
     _need(w, torch.bfloat16, "small_linear w")
     m, k = x.shape
@@ -227,6 +235,21 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
         raise RuntimeError("small_linear: bad strides/shapes")
     ldx, ldy = x.stride(0), y.stride(0)
     lib = _lib.load()
+    if k % 64 == 0 and act_out == ACT_NONE:
+        for m0 in range(0, m, 64):
+            mm = min(64, m - m0)
+            xb = torch.empty(64, k, device=x.device, dtype=torch.bfloat16)
+            _lib.check(lib.v3d_prep_small_x(x.data_ptr() + m0 * ldx * 4, ldx, xb.data_ptr(), mm, k, act_in,
+                                            _stream()), "v3d_prep_small_x")
+            g = GemmArgs()
+            g.A, g.B, g.D, g.bias = w.data_ptr(), xb.data_ptr(), y.data_ptr() + m0 * ldy * 4, _ptr(bias)
+            g.lda = g.ldb = k
+            g.ldd = ldy
+            g.batch, g.rows_per_batch, g.N, g.K, g.ntaps, g.rows_per_frame = 1, n, 64, k, 1, 1
+            g.out_fp32, g.out_transposed, g.valid_cols, g.accumulate = 1, 1, mm, 1 if accumulate else 0
+            g.s0 = g.s1 = g.s2 = 1.0
+            _lib.check(lib.v3d_gemm_bf16(C.byref(g), _stream()), "v3d_gemm_bf16(small-M)")
+        return y
     for m0 in range(0, m, 64):
         mm = min(64, m - m0)
         _lib.check(lib.v3d_small_linear(x.data_ptr() + m0 * ldx * 4, w.data_ptr(), _ptr(bias),

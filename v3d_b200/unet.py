@@ -15,6 +15,7 @@ There is no CPU path: forward on non-CUDA tensors raises.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -65,9 +66,11 @@ class KernelModule(nn.Module):
 
     def _invalidate(self) -> None:
         self._packed = None
+        if getattr(self, "_graphs", None):
+            self._graphs.clear()  # captured graphs hold pointers into the old packed weights
 
     def _apply(self, fn, recurse=True):
-        self._packed = None
+        self._invalidate()
         return super()._apply(fn, recurse)
 
     def _device(self) -> torch.device:
@@ -280,6 +283,11 @@ class VideoUNet(KernelModule):
         self._init_parameters()
         self._indicator_seen: Optional[tuple] = None
         self.debug_taps: Optional[dict] = None  # tests: {block name: None} -> filled with NCHW fp32 outputs
+        # The forward is a fixed schedule of ~1.1k launches: after one eager call per input shape it is captured
+        # into a CUDA graph and replayed (no tracing compiler involved; V3D_CUDA_GRAPH=0 disables).
+        self.cuda_graphs: bool = os.environ.get("V3D_CUDA_GRAPH", "1") != "0"
+        self._graphs: dict = {}
+        self.replayed_launches: int = 0  # kernels executed through graph replays (for launch accounting)
 
     # ------------------------------------------------------------------------------------------
     # architecture plan (execution order) and parameter table
@@ -607,9 +615,35 @@ class VideoUNet(KernelModule):
         self._check_indicator(image_only_indicator, nb, T)
         P = self.packed()
         dev = x.device
+        args = (x.float().contiguous(), timesteps.float().contiguous(),
+                context.float().reshape(B, -1).contiguous(), y.float().contiguous())
         with torch.no_grad():
-            return self._run(P, x.float().contiguous(), timesteps.float().contiguous(),
-                             context.float().reshape(B, -1).contiguous(), y.float().contiguous(), B, T, nb, H, W, dev)
+            if self.cuda_graphs and self.debug_taps is None and not torch.cuda.is_current_stream_capturing():
+                return self._run_graphed(P, args, B, T, nb, H, W, dev)
+            return self._run(P, *args, B, T, nb, H, W, dev)
+
+    def _run_graphed(self, P, args, B, T, nb, H, W, dev):
+        key = (B, T, H, W, dev.index)
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first call with this shape runs eagerly: warms kernel attributes and the positional-embedding cache
+            self._graphs[key] = "warm"
+            return self._run(P, *args, B, T, nb, H, W, dev)
+        if entry == "warm":
+            static_in = [a.clone() for a in args]
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                static_out = self._run(P, *static_in, B, T, nb, H, W, dev)
+            entry = (graph, static_in, static_out, ops.launch_count() - l0)
+            self._graphs[key] = entry
+        graph, static_in, static_out, nlaunch = entry
+        for dst, src in zip(static_in, args):
+            dst.copy_(src)
+        graph.replay()
+        self.replayed_launches += nlaunch
+        return static_out.clone()
 
     # -- embeddings that depend only on (sigma, y, context, T): computed once per forward ----------------
     def _embeddings(self, P, timesteps, ctx2d, y, B, T, dev):
@@ -618,10 +652,12 @@ class VideoUNet(KernelModule):
         ops.timestep_embedding(timesteps, t_emb, self.model_channels)
         h1 = torch.empty(B, te, device=dev)
         emb = torch.empty(B, te, device=dev)
-        ops.small_linear(t_emb, P["time_embed.0.weight"], P["time_embed.0.bias"], h1, act_out=ops.ACT_SILU)
-        ops.small_linear(h1, P["time_embed.2.weight"], P["time_embed.2.bias"], emb)
-        ops.small_linear(y, P["label_emb.0.0.weight"], P["label_emb.0.0.bias"], h1, act_out=ops.ACT_SILU)
-        ops.small_linear(h1, P["label_emb.0.2.weight"], P["label_emb.0.2.bias"], emb, accumulate=True)
+        # Linear -> SiLU -> Linear: the SiLU is applied on the consumer's input side
+        ops.small_linear(t_emb, P["time_embed.0.weight"], P["time_embed.0.bias"], h1)
+        ops.small_linear(h1, P["time_embed.2.weight"], P["time_embed.2.bias"], emb, act_in=ops.ACT_SILU)
+        ops.small_linear(y, P["label_emb.0.0.weight"], P["label_emb.0.0.bias"], h1)
+        ops.small_linear(h1, P["label_emb.0.2.weight"], P["label_emb.0.2.bias"], emb, act_in=ops.ACT_SILU,
+                         accumulate=True)
         # every ResBlock's emb_layers (SiLU -> Linear) in one launch: [B, sum(Cout)]
         emb_all = torch.empty(B, P["emb_total"], device=dev)
         ops.small_linear(emb, P["emb_all.weight"], P["emb_all.bias"], emb_all, act_in=ops.ACT_SILU)
@@ -645,9 +681,9 @@ class VideoUNet(KernelModule):
             ops.timestep_embedding(frames, t_emb, c, float(self.max_ddpm_temb_period))
             h = torch.empty(B, 4 * c, device=dev)
             out = torch.empty(B, c, device=dev)
-            ops.small_linear(t_emb, P[name + ".time_pos_embed.0.weight"], P[name + ".time_pos_embed.0.bias"], h,
-                             act_out=ops.ACT_SILU)
-            ops.small_linear(h, P[name + ".time_pos_embed.2.weight"], P[name + ".time_pos_embed.2.bias"], out)
+            ops.small_linear(t_emb, P[name + ".time_pos_embed.0.weight"], P[name + ".time_pos_embed.0.bias"], h)
+            ops.small_linear(h, P[name + ".time_pos_embed.2.weight"], P[name + ".time_pos_embed.2.bias"], out,
+                             act_in=ops.ACT_SILU)
             cache[key] = out
         return cache[key]
 
