@@ -148,7 +148,30 @@ def bench_small(out):
         out.append(dict(kind="small", name=name, ms=ms, gbs=gb))
 
 
+def one_gemm(M=147456, K=320, N=2560, geglu=True, iters=6):
+    """single shape, few launches: the target of `ncu --set full -k regex:gemm_tc`"""
+    a, w = bf(M, K), bf(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device=DEV)
+    o = torch.empty(M, N // 2 if geglu else N, device=DEV, dtype=torch.bfloat16)
+    kw = dict(K=K, N=N, rows_per_batch=M, bias=bias)
+    if geglu:
+        kw["act"] = ops.ACT_GEGLU
+    for _ in range(iters):
+        ops.gemm(a, w, o, **kw)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "one_gemm":
+        one_gemm(geglu="nogeglu" not in sys.argv)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "one_attn":
+        qkv = bf(36 * 4096, 960)
+        o = torch.empty(36 * 4096, 320, device=DEV, dtype=torch.bfloat16)
+        for _ in range(4):
+            ops.attention_spatial(qkv, o, 36, 4096, 5, 0.125)
+        torch.cuda.synchronize()
+        sys.exit(0)
     sel = set(sys.argv[1:]) or {"gemm", "conv", "attn", "norm", "small"}
     res = []
     if "gemm" in sel:
