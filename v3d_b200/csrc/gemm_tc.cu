@@ -33,7 +33,7 @@ struct GemmEpi {
   int b_batched;
   int transposed, valid_cols, accumulate;  // small-M mode: D is fp32 [cols][ldd], D[col][row]; bias per row
   // conv3x3 geometry
-  int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h;
+  int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h, bw_shift, bh_shift;
   int num_m_tiles, num_n_tiles;
   float s0, s1, s2;
 };
@@ -51,7 +51,13 @@ struct Cfg {
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool CONV>
+// epilogue variants (compile-time): what is stored and how
+constexpr int EPI_BF16 = 0;   // bf16 rows through the swizzled smem slab, coalesced stores
+constexpr int EPI_GEGLU = 1;  // value * gelu(gate) then as EPI_BF16 (linear mode only)
+constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
+constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
+
+template <int BN, bool CONV, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmEpi p) {
@@ -176,26 +182,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ------------------------------ epilogue (warps 2..9) ------------------------------
-    // Two warps per TMEM lane quarter; each takes half of the tile's 16-column chunks.  bf16 results go through a
-    // per-warp swizzled smem slab (32 rows x 128 B) and leave as row-contiguous 16-byte stores (4 full 128-byte
-    // lines per warp instruction instead of 32 half-sectors).  Residual operands of the next chunk are
-    // prefetched while the current chunk's TMEM load is in flight.
+    // Two warps per TMEM lane quarter; each takes half of the tile's 16-column chunks.  The variant (EPI) is a
+    // template parameter and the chunk loop is fully unrolled, so the per-chunk code is straight-line: TMEM load,
+    // bias/residual loads issued underneath it, math, then either the swizzled smem slab (32 rows x 128 B per
+    // warp, flushed as row-contiguous 16-byte stores: 4 full 128-byte lines per warp instruction) or direct fp32.
+    constexpr bool GEGLU = EPI == EPI_GEGLU;
+    constexpr bool STAGED = EPI == EPI_BF16 || EPI == EPI_GEGLU;
+    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+    constexpr int NCH = OUT_COLS / 16;
+    constexpr int CH_HALF = (NCH + 1) / 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
     uint8_t* stg = staging + (warp - 2) * 4096;
-    const bool geglu = p.act == V3D_ACT_GEGLU;
-    const int out_cols = geglu ? BN / 2 : BN;
-    const int nchunks = out_cols / 16;
-    const int c_begin = half ? (nchunks + 1) / 2 : 0;
-    const int c_end = half ? nchunks : (nchunks + 1) / 2;
-    const bool staged = !p.out_fp32 && !p.transposed;
+    const int c_begin = half ? CH_HALF : 0;
+    const int my_n = half ? NCH - CH_HALF : CH_HALF;
+    const bool has_bias = p.bias != nullptr;
+    const bool has_fb = p.fbias != nullptr;
+    const bool has_r1 = p.R1 != nullptr;
+    const bool has_r2 = p.R2 != nullptr;
+    const bool do_silu = p.act == V3D_ACT_SILU;
+    const float s0 = p.s0, s1 = p.s1, s2 = p.s2;
+    const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
-      // tile row -> (valid, global row); also used for other lanes' rows in the coalesced copy-out
       int t0 = 0, t1 = 0, t2 = 0;
       if (CONV) {
         t0 = (m_tile % p.tiles_w) * p.bw;
@@ -205,11 +218,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         t0 = m_tile / p.tiles_per_batch;
         t1 = (m_tile % p.tiles_per_batch) * BM;
       }
+      // tile row -> (valid, global row). bw/bh are powers of two (checked on the host).
       auto map_row = [&](int tr, long long& grow) -> bool {
         if (CONV) {
-          const int w = tr % p.bw;
-          const int h = (tr / p.bw) % p.bh;
-          const int img = t2 + tr / (p.bw * p.bh);
+          const int w = tr & (p.bw - 1);
+          const int h = (tr >> p.bw_shift) & (p.bh - 1);
+          const int img = t2 + (tr >> (p.bw_shift + p.bh_shift));
           grow = (static_cast<long long>(img) * p.ch + (t1 + h)) * p.cw + (t0 + w);
           return img < p.cn;
         } else {
@@ -220,17 +234,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       };
       long long row;
       const bool valid = map_row(r, row);
-      const float* fb = nullptr;
-      if (p.fbias != nullptr && valid) fb = p.fbias + (row / p.rows_per_frame) * p.ldfb;
-      const int obase = n_tile * out_cols;  // first output column of this tile
-      const bf16* r1p = (p.R1 != nullptr && valid) ? p.R1 + row * p.ldr1 + obase : nullptr;
-      const bf16* r2p = (p.R2 != nullptr && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
-      const float row_bias = (p.transposed && p.bias != nullptr && valid) ? __ldg(p.bias + row) : 0.f;
-
-      uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;  // residuals of the current chunk
-      if (c_begin < c_end) {
-        if (r1p) { ra0 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16)); ra1 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16) + 1); }
-        if (r2p) { rb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); rb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
+      const int obase = n_tile * OUT_COLS;  // first output column of this tile
+      const int nbase = n_tile * BN;        // first column in the (packed) N space
+      const float* fb = (has_fb && valid) ? p.fbias + (row / p.rows_per_frame) * p.ldfb + nbase : nullptr;
+      const bf16* r1p = (has_r1 && valid) ? p.R1 + row * p.ldr1 + obase : nullptr;
+      const bf16* r2p = (has_r2 && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
+      float row_bias = 0.f;
+      if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
+      // rows this lane flushes in full 4-chunk groups: rr = (lane >> 3) + 4 i, piece = lane & 7
+      long long frow[8];
+      unsigned fmask = 0;
+      if (STAGED) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (map_row(q * 32 + (lane >> 3) + 4 * i, frow[i])) fmask |= 1u << i;
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -238,127 +255,145 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t t_acc =
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
-      int grp_first = c_begin;  // first chunk of the group currently being staged
-#pragma unroll 1
-      for (int ci = c_begin; ci < c_end; ++ci) {
-        const int c = ci * 16;
-        uint32_t v[16];
-        uint32_t g[16];
-        tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
-        if (geglu) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
-        // prefetch the next chunk's residuals while the TMEM load is in flight
-        uint4 na0 = ra0, na1 = ra1, nb0 = rb0, nb1 = rb1;
-        if (ci + 1 < c_end) {
-          if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16) + 1); }
-          if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16) + 1); }
-        }
-        tmem_ld_wait();
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (valid) {
-          const int ncol = n_tile * BN + c;  // column in the (packed) N space
-          if (p.transposed) {
+      for (int k = 0; k < CH_HALF; ++k) {
+        if (k < my_n) {
+          const int c = (c_begin + k) * 16;
+          uint32_t v[16];
+          uint32_t g[16];
+          tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
+          if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
+          // operand loads issued while the TMEM load is in flight
+          float4 bv[4], bg[4], fv[4];
+          uint4 ra0, ra1, rb0, rb1;
+          if (EPI != EPI_TRANS && has_bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
+            if (GEGLU) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bg[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + BN / 2 + c) + j);
+            }
+          }
+          if (fb) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fv[j] = __ldg(reinterpret_cast<const float4*>(fb + c) + j);
+          }
+          if (r1p) { ra0 = __ldg(reinterpret_cast<const uint4*>(r1p + c)); ra1 = __ldg(reinterpret_cast<const uint4*>(r1p + c) + 1); }
+          if (r2p) { rb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c)); rb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c) + 1); }
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (EPI == EPI_TRANS) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += row_bias;
-          } else if (p.bias != nullptr) {
+          } else if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
+            for (int j = 0; j < 4; ++j) { f[4 * j] += bv[j].x; f[4 * j + 1] += bv[j].y; f[4 * j + 2] += bv[j].z; f[4 * j + 3] += bv[j].w; }
           }
-          if (fb != nullptr) {
+          if (fb) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(fb + ncol + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
+            for (int j = 0; j < 4; ++j) { f[4 * j] += fv[j].x; f[4 * j + 1] += fv[j].y; f[4 * j + 2] += fv[j].z; f[4 * j + 3] += fv[j].w; }
           }
-          if (geglu) {
+          if (GEGLU) {
             float gt[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
-            if (p.bias != nullptr) {
+            if (has_bias) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + BN / 2 + j));
-                gt[j] += b4.x; gt[j + 1] += b4.y; gt[j + 2] += b4.z; gt[j + 3] += b4.w;
-              }
+              for (int j = 0; j < 4; ++j) { gt[4 * j] += bg[j].x; gt[4 * j + 1] += bg[j].y; gt[4 * j + 2] += bg[j].z; gt[4 * j + 3] += bg[j].w; }
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_fast(gt[j]);
-          } else if (p.act == V3D_ACT_SILU) {
+          } else if (EPI == EPI_F32 && do_silu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
           }
+          if (r1p || r2p) {
+            float t[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] *= p.s0;
-          if (r1p) {
-            const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
+            for (int j = 0; j < 16; ++j) t[j] = 0.f;
+            if (r1p) {
+              const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 t = unpack_bf16x2(u[j]);
-              f[2 * j] += p.s1 * t.x;
-              f[2 * j + 1] += p.s1 * t.y;
+              for (int j = 0; j < 8; ++j) {
+                const float2 x2 = unpack_bf16x2(u[j]);
+                t[2 * j] = s1 * x2.x;
+                t[2 * j + 1] = s1 * x2.y;
+              }
             }
-          }
-          if (r2p) {
-            const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
+            if (r2p) {
+              const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 t = unpack_bf16x2(u[j]);
-              f[2 * j] += p.s2 * t.x;
-              f[2 * j + 1] += p.s2 * t.y;
+              for (int j = 0; j < 8; ++j) {
+                const float2 x2 = unpack_bf16x2(u[j]);
+                t[2 * j] = fmaf(s2, x2.x, t[2 * j]);
+                t[2 * j + 1] = fmaf(s2, x2.y, t[2 * j + 1]);
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s0, t[j]);
+          } else if (s0 != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= s0;
           }
-          const int ocol = obase + c;
-          if (p.transposed) {
+          if (EPI == EPI_TRANS) {
             // D[col][row]: lanes hold consecutive rows -> each store instruction is one contiguous 128-byte line
-            float* dp = static_cast<float*>(p.D) + row;
+            if (valid) {
+              float* dp = static_cast<float*>(p.D) + row;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (ocol + j < p.valid_cols) {
-                float* o = dp + static_cast<long long>(ocol + j) * p.ldd;
-                *o = p.accumulate ? *o + f[j] : f[j];
+              for (int j = 0; j < 16; ++j) {
+                if (obase + c + j < p.valid_cols) {
+                  float* o = dp + static_cast<long long>(obase + c + j) * p.ldd;
+                  *o = p.accumulate ? *o + f[j] : f[j];
+                }
               }
             }
-          } else if (p.out_fp32) {
-            float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + ocol);
+          } else if (EPI == EPI_F32) {
+            if (valid) {
+              float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + obase + c);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-        }
-        if (staged) {
-          // stage this chunk (2 x 16 B) into the warp's slab at 16-byte slots (2k, 2k+1) of row `lane`
-          const int k = ci - grp_first;
-          uint8_t* srow = stg + lane * 128;
-          const int sw = lane & 7;
-          *reinterpret_cast<uint4*>(srow + (((2 * k) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          *reinterpret_cast<uint4*>(srow + (((2 * k + 1) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-          if (k == 3 || ci + 1 == c_end) {
-            // flush the group: (k+1) chunks = 2(k+1) 16-byte pieces per row, rows contiguous in global memory
-            __syncwarp();
-            const int ppr = 2 * (k + 1);
-            const int total = 32 * ppr;
-            const int gcol = obase + grp_first * 16;
-            for (int idx = lane; idx < total; idx += 32) {
-              const int rr = idx / ppr;
-              const int piece = idx - rr * ppr;
-              long long grow;
-              if (map_row(q * 32 + rr, grow)) {
-                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
-                *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
-              }
+              for (int j = 0; j < 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
-            __syncwarp();
-            grp_first = ci + 1;
+          } else {
+            // stage this chunk (2 x 16 B) into the warp's slab at 16-byte slots (2kk, 2kk+1) of row `lane`
+            const int kk = k & 3;
+            uint8_t* srow = stg + lane * 128;
+            *reinterpret_cast<uint4*>(srow + (((2 * kk) ^ sw) << 4)) =
+                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(srow + (((2 * kk + 1) ^ sw) << 4)) =
+                make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            const int gcol = obase + (c_begin + (k & ~3)) * 16;  // first column of the group being staged
+            if (kk == 3) {
+              // full group: 8 pieces per row; this lane owns piece (lane & 7) of rows (lane >> 3) + 4 i
+              __syncwarp();
+              const int piece = lane & 7;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = (lane >> 3) + 4 * i;
+                if (fmask & (1u << i)) {
+                  const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + frow[i] * p.ldd + gcol + piece * 8) = val;
+                }
+              }
+              __syncwarp();
+            } else if (k + 1 == my_n) {
+              // tail group of (kk+1) chunks: generic mapping
+              __syncwarp();
+              const int ppr = 2 * (kk + 1);
+              for (int idx = lane; idx < 32 * ppr; idx += 32) {
+                const int rr = idx / ppr;
+                const int piece = idx - rr * ppr;
+                long long grow;
+                if (map_row(q * 32 + rr, grow)) {
+                  const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
+                }
+              }
+              __syncwarp();
+            }
           }
         }
-        ra0 = na0; ra1 = na1; rb0 = nb0; rb1 = nb1;
       }
       tc_fence_before();
       __syncwarp();
@@ -391,11 +426,11 @@ static int pick_block_n(int N, int act) {
   return 0;
 }
 
-template <int BN, bool CONV>
+template <int BN, bool CONV, int EPI>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, CONV>;
+  auto kern = gemm_tc_kernel<BN, CONV, EPI>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -411,16 +446,33 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& e
   return V3D_OK;
 }
 
+template <int BN, bool CONV>
+static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
+                        cudaStream_t st) {
+  switch (epi_kind) {
+    case EPI_BF16: return launch<BN, CONV, EPI_BF16>(ma, mb, epi, st);
+    case EPI_F32: return launch<BN, CONV, EPI_F32>(ma, mb, epi, st);
+    case EPI_GEGLU:
+      if constexpr (!CONV && (BN / 2) % 16 == 0) return launch<BN, false, EPI_GEGLU>(ma, mb, epi, st);
+      break;
+    case EPI_TRANS:
+      if constexpr (!CONV) return launch<BN, false, EPI_TRANS>(ma, mb, epi, st);
+      break;
+  }
+  set_error("unsupported epilogue %d for this mode/tile", epi_kind);
+  return V3D_ERR_BAD_ARG;
+}
+
 template <bool CONV>
-static int dispatch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
+static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
                        cudaStream_t st) {
   switch (bn) {
-    case 256: return launch<256, CONV>(ma, mb, epi, st);
-    case 160: return launch<160, CONV>(ma, mb, epi, st);
-    case 128: return launch<128, CONV>(ma, mb, epi, st);
-    case 64: return launch<64, CONV>(ma, mb, epi, st);
-    case 32: return launch<32, CONV>(ma, mb, epi, st);
-    case 16: return launch<16, CONV>(ma, mb, epi, st);
+    case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, epi, st);
+    case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, epi, st);
+    case 128: return dispatch_epi<128, CONV>(epi_kind, ma, mb, epi, st);
+    case 64: return dispatch_epi<64, CONV>(epi_kind, ma, mb, epi, st);
+    case 32: return dispatch_epi<32, CONV>(epi_kind, ma, mb, epi, st);
+    case 16: return dispatch_epi<16, CONV>(epi_kind, ma, mb, epi, st);
     default: set_error("unsupported block_n %d", bn); return V3D_ERR_BAD_ARG;
   }
 }
@@ -524,7 +576,13 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       return V3D_ERR_UNSUPPORTED;
     }
     const int bnimg = BM / (bw * bh);
+    if ((bw & (bw - 1)) != 0 || (bh & (bh - 1)) != 0) {
+      set_error("conv3x3: tile box %dx%d is not a power of two", bw, bh);
+      return V3D_ERR_UNSUPPORTED;
+    }
     e.cn = NI; e.ch = H; e.cw = W; e.bw = bw; e.bh = bh; e.bn = bnimg;
+    e.bw_shift = __builtin_ctz(bw);
+    e.bh_shift = __builtin_ctz(bh);
     e.tiles_w = W / bw;
     e.tiles_h = H / bh;
     e.num_m_tiles = e.tiles_w * e.tiles_h * ((NI + bnimg - 1) / bnimg);
@@ -568,5 +626,13 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return conv ? dispatch_bn<true>(bn, ma, mb, e, st) : dispatch_bn<false>(bn, ma, mb, e, st);
+  int epi_kind = EPI_BF16;
+  if (a->out_transposed) epi_kind = EPI_TRANS;
+  else if (a->out_fp32) epi_kind = EPI_F32;
+  else if (a->act == V3D_ACT_GEGLU) epi_kind = EPI_GEGLU;
+  if ((a->act == V3D_ACT_GEGLU && epi_kind != EPI_GEGLU) || (a->act == V3D_ACT_SILU && epi_kind != EPI_F32)) {
+    set_error("v3d_gemm_bf16: act=%d is not available with this output mode", a->act);
+    return V3D_ERR_UNSUPPORTED;
+  }
+  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, e, st) : dispatch_bn<false>(bn, epi_kind, ma, mb, e, st);
 }

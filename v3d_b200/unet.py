@@ -53,7 +53,9 @@ def conv_tiles_ok(h: int, w: int) -> bool:
     if 128 % bw or w % bw:
         return False
     bh = min(128 // bw, h)
-    return h % bh == 0 and (128 // bw) % bh == 0
+    if h % bh or (128 // bw) % bh:
+        return False
+    return bw & (bw - 1) == 0 and bh & (bh - 1) == 0
 
 
 class KernelModule(nn.Module):
