@@ -241,6 +241,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bf16* r2p = (has_r2 && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
       float row_bias = 0.f;
       if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
+      if (has_r1 || has_r2) {
+        // pull the NEXT tile's residual row segments into L2 now; they are consumed one tile-time later
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int nn = nt % p.num_n_tiles, nm = nt / p.num_n_tiles;
+          int u0, u1, u2 = 0;
+          if (CONV) {
+            u0 = (nm % p.tiles_w) * p.bw;
+            u1 = ((nm / p.tiles_w) % p.tiles_h) * p.bh;
+            u2 = (nm / (p.tiles_w * p.tiles_h)) * p.bn;
+          } else {
+            u0 = nm / p.tiles_per_batch;
+            u1 = (nm % p.tiles_per_batch) * BM;
+          }
+          long long nrow;
+          bool nvalid;
+          if (CONV) {
+            const int w = r & (p.bw - 1);
+            const int h = (r >> p.bw_shift) & (p.bh - 1);
+            const int img = u2 + (r >> (p.bw_shift + p.bh_shift));
+            nrow = (static_cast<long long>(img) * p.ch + (u1 + h)) * p.cw + (u0 + w);
+            nvalid = img < p.cn;
+          } else {
+            nrow = static_cast<long long>(u0) * p.rows_per_batch + u1 + r;
+            nvalid = u1 + r < p.rows_per_batch;
+          }
+          if (nvalid) {
+            const int ncol0 = nn * OUT_COLS + c_begin * 16;
+#pragma unroll
+            for (int off = 0; off < CH_HALF * 16; off += 64) {
+              if (has_r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + nrow * p.ldr1 + ncol0 + off));
+              if (has_r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R2 + nrow * p.ldr2 + ncol0 + off));
+            }
+          }
+        }
+      }
       // rows this lane flushes in full 4-chunk groups: rr = (lane >> 3) + 4 i, piece = lane & 7
       long long frow[8];
       unsigned fmask = 0;
@@ -255,6 +291,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t t_acc =
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
+      // residuals: chunk 0 now, chunk k+1 while chunk k is processed (8 + 8 registers in flight)
+      uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nb0 = na0, nb1 = na0;
+      if (my_n > 0) {
+        if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16) + 1); }
+        if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
+      }
 #pragma unroll
       for (int k = 0; k < CH_HALF; ++k) {
         if (k < my_n) {
@@ -265,7 +307,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
           // operand loads issued while the TMEM load is in flight
           float4 bv[4], bg[4], fv[4];
-          uint4 ra0, ra1, rb0, rb1;
+          const uint4 ra0 = na0, ra1 = na1, rb0 = nb0, rb1 = nb1;
+          if (k + 1 < my_n) {
+            if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16) + 1); }
+            if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16) + 1); }
+          }
           if (EPI != EPI_TRANS && has_bias) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
@@ -278,8 +324,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 4; ++j) fv[j] = __ldg(reinterpret_cast<const float4*>(fb + c) + j);
           }
-          if (r1p) { ra0 = __ldg(reinterpret_cast<const uint4*>(r1p + c)); ra1 = __ldg(reinterpret_cast<const uint4*>(r1p + c) + 1); }
-          if (r2p) { rb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c)); rb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c) + 1); }
           tmem_ld_wait();
           float f[16];
 #pragma unroll
