@@ -163,7 +163,11 @@ def one_gemm(M=147456, K=320, N=2560, geglu=True, iters=6):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one_gemm":
-        one_gemm(geglu="nogeglu" not in sys.argv)
+        nums = [int(a) for a in sys.argv[2:] if a.isdigit()]
+        if len(nums) == 3:
+            one_gemm(nums[0], nums[1], nums[2], geglu="geglu" in sys.argv)
+        else:
+            one_gemm(geglu="nogeglu" not in sys.argv)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one_attn":
         qkv = bf(36 * 4096, 960)
