@@ -240,19 +240,33 @@ attn_spatial_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, cons
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxT = 32;
 constexpr int kTaWarps = 4;
-constexpr int kTaRowB = 144;  // 128 B of data + 16 B pad per staged row
+constexpr int kTaTile = 32 * 128;  // one [32 rows][64] bf16 tile, 128-byte rows, XOR-swizzled 16-byte chunks
 
+// Temporal attention over T <= 32 frames: one warp per (pixel, head) sequence, whole problem on tensor cores:
+//   S (32x32, keys >= T masked) = Q K^T   : 2 m-tiles x 4 n-tiles x 4 k-steps of mma.m16n8k16
+//   O (32x64)                  = P V      : 2 m-tiles x 8 n-tiles x 2 k-steps
+// Q/K/V rows are gathered with the frame stride S*ld straight from the frame-major token matrix (cp.async,
+// 16-byte chunks), O is staged through the Q tile and written back as 16-byte chunks.
 __global__ void __launch_bounds__(kTaWarps * 32)
 attn_temporal_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf16* __restrict__ V,
                      bf16* __restrict__ O, long long ld, long long ldo, int T, int S, int nheads,
-                     float scale) {
-  __shared__ __align__(16) uint8_t ta_smem[kTaWarps * 2 * kMaxT * kTaRowB];
+                     float scale_log2e) {
+  extern __shared__ __align__(128) uint8_t ta_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int s = blockIdx.x, b = blockIdx.y;
-  uint8_t* wk = ta_smem + static_cast<size_t>(warp) * 2 * kMaxT * kTaRowB;
-  uint8_t* wv = wk + kMaxT * kTaRowB;
+  uint8_t* sq = ta_smem + warp * 3 * kTaTile;
+  uint8_t* sk = sq + kTaTile;
+  uint8_t* sv = sk + kTaTile;
   const long long row_base = (static_cast<long long>(b) * T) * S + s;
-  const bool active = lane < T;
+
+  // rows >= T of K and V are never loaded: zero them once (P is 0 there, but 0 * garbage must stay 0)
+  for (int i = lane; i < (32 - T) * 8; i += 32) {
+    const int r = T + (i >> 3), c = i & 7;
+    *reinterpret_cast<uint4*>(sk + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sv + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sq + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+  }
 
   for (int head = warp; head < nheads; head += kTaWarps) {
     const long long col = static_cast<long long>(head) * HD;
@@ -260,84 +274,127 @@ attn_temporal_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, con
     for (int i = lane; i < T * 8; i += 32) {
       const int r = i >> 3, c = i & 7;
       const long long off = (row_base + static_cast<long long>(r) * S) * ld + col + c * 8;
-      *reinterpret_cast<uint4*>(wk + r * kTaRowB + c * 16) = __ldg(reinterpret_cast<const uint4*>(K + off));
-      *reinterpret_cast<uint4*>(wv + r * kTaRowB + c * 16) = __ldg(reinterpret_cast<const uint4*>(V + off));
+      cp_async16(sq + tile_off(r, c), Q + off, true);
+      cp_async16(sk + tile_off(r, c), K + off, true);
+      cp_async16(sv + tile_off(r, c), V + off, true);
     }
-    float p[kMaxT];
-    {
-      float q[HD];
-      const long long off = (row_base + static_cast<long long>(active ? lane : 0) * S) * ld + col;
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // ---- S = Q K^T
+    float sc[2][4][4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(Q + off + c * 8));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          q[c * 8 + 2 * j] = f.x * scale;
-          q[c * 8 + 2 * j + 1] = f.y * scale;
-        }
-      }
-      __syncwarp();
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int j = 0; j < kMaxT; ++j) {
-        float acc = -INFINITY;
-        if (j < T) {
-          acc = 0.f;
+        for (int e = 0; e < 4; ++e) sc[mt][j][e] = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(wk + j * kTaRowB + c * 16);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t qa[2][4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(w[e]);
-              acc = fmaf(q[c * 8 + 2 * e], f.x, acc);
-              acc = fmaf(q[c * 8 + 2 * e + 1], f.y, acc);
-            }
-          }
-        }
-        p[j] = acc;
-      }
-    }
-    float mx = -INFINITY;
+      for (int mt = 0; mt < 2; ++mt)
+        ldsm_x4(smem_u32(sq + tile_off(mt * 16 + (lane & 15), kk * 2 + (lane >> 4))), qa[mt][0], qa[mt][1],
+                qa[mt][2], qa[mt][3]);
 #pragma unroll
-    for (int j = 0; j < kMaxT; ++j) mx = fmaxf(mx, p[j]);
-    float sum = 0.f;
+      for (int jp = 0; jp < 2; ++jp) {  // pairs of key n-tiles
+        const int mi = lane >> 3;
+        const int key = jp * 16 + (mi >> 1) * 8 + (lane & 7);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(sk + tile_off(key, kk * 2 + (mi & 1))), b0, b1, b2, b3);
 #pragma unroll
-    for (int j = 0; j < kMaxT; ++j) {
-      p[j] = __expf(p[j] - mx);  // exp(-inf) = 0 for j >= T
-      sum += p[j];
-    }
-    const float inv = 1.f / sum;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < kMaxT; ++j) {
-      if (j < T) {
-        // P is rounded to bf16 before P.V, matching the tensor-core attention kernels
-        const float pj = __bfloat162float(__float2bfloat16_rn(p[j] * inv));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = *reinterpret_cast<const uint4*>(wv + j * kTaRowB + c * 16);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack_bf16x2(w[e]);
-            o[c * 8 + 2 * e] = fmaf(pj, f.x, o[c * 8 + 2 * e]);
-            o[c * 8 + 2 * e + 1] = fmaf(pj, f.y, o[c * 8 + 2 * e + 1]);
-          }
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(sc[mt][2 * jp], qa[mt], b0, b1);
+          mma_bf16_16816(sc[mt][2 * jp + 1], qa[mt], b2, b3);
         }
       }
     }
-    if (active) {
-      bf16* op = O + (row_base + static_cast<long long>(lane) * S) * ldo + col;
+    // ---- softmax over keys (columns), rows g / g+8 of each m-tile; P packed as A fragments
+    uint32_t pf[2][2][4];
+    float inv[2][2];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        *reinterpret_cast<uint4*>(op + c * 8) =
-            make_uint4(pack_bf16x2(o[c * 8], o[c * 8 + 1]), pack_bf16x2(o[c * 8 + 2], o[c * 8 + 3]),
-                       pack_bf16x2(o[c * 8 + 4], o[c * 8 + 5]), pack_bf16x2(o[c * 8 + 6], o[c * 8 + 7]));
+    for (int mt = 0; mt < 2; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = j * 8 + 2 * t;
+        if (key >= T) { sc[mt][j][0] = -INFINITY; sc[mt][j][2] = -INFINITY; }
+        if (key + 1 >= T) { sc[mt][j][1] = -INFINITY; sc[mt][j][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(sc[mt][j][0], sc[mt][j][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[mt][j][2], sc[mt][j][3]));
       }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0 = mx0 * scale_log2e, m1 = mx1 * scale_log2e;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p0 = exp2f(fmaf(sc[mt][j][0], scale_log2e, -m0));
+        const float p1 = exp2f(fmaf(sc[mt][j][1], scale_log2e, -m0));
+        const float p2 = exp2f(fmaf(sc[mt][j][2], scale_log2e, -m1));
+        const float p3 = exp2f(fmaf(sc[mt][j][3], scale_log2e, -m1));
+        s0 += p0 + p1;
+        s1 += p2 + p3;
+        const int kk = j >> 1;
+        if ((j & 1) == 0) {
+          pf[mt][kk][0] = pack_bf16x2(p0, p1);
+          pf[mt][kk][1] = pack_bf16x2(p2, p3);
+        } else {
+          pf[mt][kk][2] = pack_bf16x2(p0, p1);
+          pf[mt][kk][3] = pack_bf16x2(p2, p3);
+        }
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      inv[mt][0] = 1.f / s0;
+      inv[mt][1] = 1.f / s1;
+    }
+    // ---- O = P V
+    float oc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oc[mt][j][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // pairs of d n-tiles
+        const int mi = lane >> 3;
+        const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(sv + tile_off(key, jp * 2 + (mi >> 1))), b0, b1, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(oc[mt][2 * jp], pf[mt][kk], b0, b1);
+          mma_bf16_16816(oc[mt][2 * jp + 1], pf[mt][kk], b2, b3);
+        }
+      }
+    }
+    // ---- stage O (normalised, bf16) through the Q tile, then 16-byte row-chunk stores
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r0 = mt * 16 + g;
+        const int colb = (j * 8 + 2 * t) * 2;  // byte offset inside the 128-byte row
+        *reinterpret_cast<uint32_t*>(sq + tile_off(r0, colb >> 4) + (colb & 15)) =
+            pack_bf16x2(oc[mt][j][0] * inv[mt][0], oc[mt][j][1] * inv[mt][0]);
+        *reinterpret_cast<uint32_t*>(sq + tile_off(r0 + 8, colb >> 4) + (colb & 15)) =
+            pack_bf16x2(oc[mt][j][2] * inv[mt][1], oc[mt][j][3] * inv[mt][1]);
+      }
+    __syncwarp();
+    for (int i = lane; i < T * 8; i += 32) {
+      const int r = i >> 3, c = i & 7;
+      *reinterpret_cast<uint4*>(O + (row_base + static_cast<long long>(r) * S) * ldo + col + c * 8) =
+          *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
     }
   }
 }
@@ -396,10 +453,11 @@ int v3d_attention_temporal(const void* q, const void* k, const void* v, void* o,
     return V3D_ERR_BAD_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem = kTaWarps * 3 * kTaTile;
   dim3 grid(S, nb);
-  attn_temporal_kernel<<<grid, kTaWarps * 32, 0, st>>>(
+  attn_temporal_kernel<<<grid, kTaWarps * 32, smem, st>>>(
       static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
-      static_cast<bf16*>(o), ld_qkv, ld_o, T, S, nheads, scale);
+      static_cast<bf16*>(o), ld_qkv, ld_o, T, S, nheads, scale * 1.44269504088896340736f);
   V3D_CHECK_LAUNCH("attn_temporal_kernel");
   return V3D_OK;
 }

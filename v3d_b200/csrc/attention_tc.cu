@@ -135,24 +135,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       tc_fence_after();
       const int kbase = j * AT_BN;
       const bool tail = kbase + AT_BN > ntok;
+      // TMEM loads are double-buffered: chunk c+1 is requested before chunk c is processed
+      uint32_t va[32], vb[32];
       // ---- pass 1: row max
       float mx = -INFINITY;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_base + static_cast<uint32_t>(c4 * 32), v);
-        tmem_ld_wait();
+      auto scan_max = [&](const uint32_t (&v)[32], int c4) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (tail && kbase + c4 * 32 + i >= ntok) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          float sv = __uint_as_float(v[i]);
+          if (tail && kbase + c4 * 32 + i >= ntok) sv = -INFINITY;
+          mx = fmaxf(mx, sv);
         }
-      }
+      };
+      tmem_ld32(tS + lane_base, va);
+      tmem_ld_wait();
+      tmem_ld32(tS + lane_base + 32u, vb);
+      scan_max(va, 0);
+      tmem_ld_wait();
+      tmem_ld32(tS + lane_base + 64u, va);
+      scan_max(vb, 1);
+      tmem_ld_wait();
+      tmem_ld32(tS + lane_base + 96u, vb);
+      scan_max(va, 2);
+      tmem_ld_wait();
+      // first chunk of pass 2 is requested while the last max chunk is reduced
+      tmem_ld32(tS + lane_base, va);
+      scan_max(vb, 3);
       const float m_new = fmaxf(m_run, mx);
-      const float corr = exp2f((m_run - m_new) * scale_log2e);  // 0 on the first tile
+      const float corr = ex2_approx((m_run - m_new) * scale_log2e);  // 0 on the first tile
       const float msc = m_new * scale_log2e;
       m_run = m_new;
+      tmem_ld_wait();  // pass-2 chunk 0 has landed in va
       // ---- fold O_{j-1} into the register accumulator (PV_{j-1} was issued before S_j, so it has completed)
       if (j > 0) {
         const int pj = j - 1;
@@ -160,25 +173,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         tc_fence_after();
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t v[32];
-          tmem_ld32(tO + lane_base + static_cast<uint32_t>((pj & 1) * 64 + c2 * 32), v);
+          tmem_ld32(tO + lane_base + static_cast<uint32_t>((pj & 1) * 64 + c2 * 32), vb);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c2 * 32 + i] = (acc[c2 * 32 + i] + __uint_as_float(v[i])) * corr;
+          for (int i = 0; i < 32; ++i) acc[c2 * 32 + i] = (acc[c2 * 32 + i] + __uint_as_float(vb[i])) * corr;
         }
       }
       // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P into the swizzled smem A-operand tile
       float l_tile = 0.f;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_base + static_cast<uint32_t>(c4 * 32), v);
-        tmem_ld_wait();
+      auto emit_p = [&](const uint32_t (&v)[32], int c4) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[i]), scale_log2e, -msc));
-          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -msc));
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2e, -msc));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -msc));
           if (tail) {
             if (kbase + c4 * 32 + i >= ntok) p0 = 0.f;
             if (kbase + c4 * 32 + i + 1 >= ntok) p1 = 0.f;
@@ -194,7 +202,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           *reinterpret_cast<uint4*>(pa + ((chunk ^ sw) << 4)) =
               make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
-      }
+      };
+      tmem_ld32(tS + lane_base + 32u, vb);
+      emit_p(va, 0);
+      tmem_ld_wait();
+      tmem_ld32(tS + lane_base + 64u, va);
+      emit_p(vb, 1);
+      tmem_ld_wait();
+      tmem_ld32(tS + lane_base + 96u, vb);
+      emit_p(va, 2);
+      tmem_ld_wait();
+      emit_p(vb, 3);
       l_run = l_run * corr + l_tile;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();

@@ -58,7 +58,7 @@ constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
 
 template <int BN, bool CONV, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(200)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmEpi p) {
   using C = Cfg<BN>;
@@ -297,14 +297,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16) + 1); }
         if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
       }
+      // TMEM accumulator chunks are double-buffered: chunk k+1 is requested as soon as chunk k has landed
+      uint32_t vbuf[2][16];
+      uint32_t gbuf[2][16];
+      if (my_n > 0) {
+        tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
+        if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c_begin * 16), gbuf[0]);
+      }
 #pragma unroll
       for (int k = 0; k < CH_HALF; ++k) {
         if (k < my_n) {
           const int c = (c_begin + k) * 16;
-          uint32_t v[16];
-          uint32_t g[16];
-          tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
-          if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
+          uint32_t (&v)[16] = vbuf[k & 1];
+          uint32_t (&g)[16] = gbuf[k & 1];
           // operand loads issued while the TMEM load is in flight
           float4 bv[4], bg[4], fv[4];
           const uint4 ra0 = na0, ra1 = na1, rb0 = nb0, rb1 = nb1;
@@ -328,6 +333,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          float gt[16];
+          if (GEGLU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
+          }
+          if (k + 1 < my_n) {
+            tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[(k + 1) & 1]);
+            if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c + 16), gbuf[(k + 1) & 1]);
+          }
           if (EPI == EPI_TRANS) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += row_bias;
@@ -340,9 +354,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 4; ++j) { f[4 * j] += fv[j].x; f[4 * j + 1] += fv[j].y; f[4 * j + 2] += fv[j].z; f[4 * j + 3] += fv[j].w; }
           }
           if (GEGLU) {
-            float gt[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
             if (has_bias) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) { gt[4 * j] += bg[j].x; gt[4 * j + 1] += bg[j].y; gt[4 * j + 2] += bg[j].z; gt[4 * j + 3] += bg[j].w; }
