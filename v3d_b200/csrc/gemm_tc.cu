@@ -58,7 +58,7 @@ constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
 
 template <int BN, bool CONV, int EPI>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmEpi p) {
   using C = Cfg<BN>;
