@@ -58,7 +58,7 @@ constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
 
 template <int BN, bool CONV, int EPI>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const GemmEpi p) {
   using C = Cfg<BN>;
@@ -277,15 +277,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
-      // rows this lane flushes in full 4-chunk groups: rr = (lane >> 3) + 4 i, piece = lane & 7
-      long long frow[8];
-      unsigned fmask = 0;
-      if (STAGED) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (map_row(q * 32 + (lane >> 3) + 4 * i, frow[i])) fmask |= 1u << i;
-      }
-
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc =
@@ -298,18 +289,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
       }
       // TMEM accumulator chunks are double-buffered: chunk k+1 is requested as soon as chunk k has landed
-      uint32_t vbuf[2][16];
-      uint32_t gbuf[2][16];
-      if (my_n > 0) {
-        tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
-        if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c_begin * 16), gbuf[0]);
-      }
+      // (GEGLU tiles load value+gate per chunk without the double buffer: register budget)
+      constexpr int NBUF = GEGLU ? 1 : 2;
+      uint32_t vbuf[NBUF][16];
+      uint32_t gbuf[1][16];
+      if (my_n > 0 && !GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
 #pragma unroll
       for (int k = 0; k < CH_HALF; ++k) {
         if (k < my_n) {
           const int c = (c_begin + k) * 16;
-          uint32_t (&v)[16] = vbuf[k & 1];
-          uint32_t (&g)[16] = gbuf[k & 1];
+          uint32_t (&v)[16] = vbuf[GEGLU ? 0 : (k & 1)];
+          uint32_t (&g)[16] = gbuf[0];
+          if (GEGLU) {
+            tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
+            tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
+          }
           // operand loads issued while the TMEM load is in flight
           float4 bv[4], bg[4], fv[4];
           const uint4 ra0 = na0, ra1 = na1, rb0 = nb0, rb1 = nb1;
@@ -338,10 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
           }
-          if (k + 1 < my_n) {
-            tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[(k + 1) & 1]);
-            if (GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c + 16), gbuf[(k + 1) & 1]);
-          }
+          if (!GEGLU && k + 1 < my_n) tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[GEGLU ? 0 : ((k + 1) & 1)]);
           if (EPI == EPI_TRANS) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += row_bias;
@@ -426,9 +417,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rr = (lane >> 3) + 4 * i;
-                if (fmask & (1u << i)) {
+                long long grow;
+                if (map_row(q * 32 + rr, grow)) {
                   const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
-                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + frow[i] * p.ldd + gcol + piece * 8) = val;
+                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
                 }
               }
               __syncwarp();
