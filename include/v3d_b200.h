@@ -99,9 +99,10 @@ int v3d_gemm_pick_block_n(int32_t N, int32_t act);
  * ------------------------------------------------------------------------------------------ */
 /* stats: double [nsamples][groups][2] = {sum, sumsq} over rows_per_sample x (C/groups). rows_per_sample is
  * H*W for 2-D norms (util.py:259-276; attention.py:130-133; model.py:52-55) and T*H*W for the 3-D
- * time_stack ResBlock norms (openaimodel.py:267-271 with dims=3). */
+ * time_stack ResBlock norms (openaimodel.py:267-271 with dims=3). The kernel accumulates with atomics: stats is
+ * cleared first unless pre_zeroed != 0 (callers that carve many stats slices out of one zeroed pool). */
 int v3d_groupnorm_stats(const void* x, void* stats, int64_t rows_per_sample, int32_t nsamples, int32_t C,
-                        int32_t ldx, int32_t groups, void* stream);
+                        int32_t ldx, int32_t groups, int32_t pre_zeroed, void* stream);
 /* y (dense, ld = C) = act(GN(x)); silu != 0 fuses the nn.SiLU / nonlinearity that always follows
  * (openaimodel.py:267-271,300-303; model.py:131-143). */
 int v3d_groupnorm_apply(const void* x, void* y, const void* stats, const void* gamma, const void* beta,

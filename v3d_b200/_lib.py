@@ -46,7 +46,7 @@ SIGNATURES = {
     "v3d_geglu_pack_rows": (C.c_int, [_i32, _i32, C.POINTER(C.c_int32)]),
     "v3d_gemm_pick_block_n": (C.c_int, [_i32, _i32]),
     # norm.cu
-    "v3d_groupnorm_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "v3d_groupnorm_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "v3d_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "v3d_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
     "v3d_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp]),

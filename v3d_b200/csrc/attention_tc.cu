@@ -10,6 +10,8 @@
 //                 O_{j-1} pulled from TMEM and folded into a register accumulator with the running-max correction.
 // TMEM per CTA: 256 columns; shared memory ~112 KB -> two CTAs per SM interleave (one in softmax while the
 // other's MMAs run), which is what hides the single-CTA S -> softmax -> PV dependency chain.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.cuh"
 #include "v3d_b200.h"
@@ -126,25 +128,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint8_t* prow = smem + AT_OFF_P + r * 128;
     const int sw = r & 7;
     float m_run = -INFINITY, l_run = 0.f;
-    float acc[64];
+    uint64_t acc[32];  // O accumulator, 64 fp32 as 32 packed pairs (FFMA2/FADD2/FMUL2 halve the issue slots)
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0ull;
+    const uint64_t sl2 = pack2(scale_log2e, scale_log2e);
 
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
+    // One 128-key tile. TAIL = the tile crosses ntok: keys beyond it are masked (only the last tile can be one).
+    auto softmax_tile = [&](int j, auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
       const int kbase = j * AT_BN;
-      const bool tail = kbase + AT_BN > ntok;
-      // TMEM loads are double-buffered: chunk c+1 is requested before chunk c is processed
-      uint32_t va[32], vb[32];
-      // ---- pass 1: row max
+      uint32_t va[32], vb[32];  // double-buffered TMEM chunks
+      // ---- pass 1: row max (FMNMX3: two elements per instruction)
       float mx = -INFINITY;
       auto scan_max = [&](const uint32_t (&v)[32], int c4) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(v[i]);
-          if (tail && kbase + c4 * 32 + i >= ntok) sv = -INFINITY;
-          mx = fmaxf(mx, sv);
+        for (int i = 0; i < 32; i += 2) {
+          float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]);
+          if (TAIL) {
+            if (kbase + c4 * 32 + i >= ntok) a0 = -INFINITY;
+            if (kbase + c4 * 32 + i + 1 >= ntok) a1 = -INFINITY;
+          }
+          mx = fmaxf(fmaxf(a0, a1), mx);
         }
       };
       tmem_ld32(tS + lane_base, va);
@@ -158,40 +162,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       tmem_ld32(tS + lane_base + 96u, vb);
       scan_max(va, 2);
       tmem_ld_wait();
-      // first chunk of pass 2 is requested while the last max chunk is reduced
-      tmem_ld32(tS + lane_base, va);
+      tmem_ld32(tS + lane_base, va);  // first chunk of pass 2, requested while the last max chunk is reduced
       scan_max(vb, 3);
       const float m_new = fmaxf(m_run, mx);
       const float corr = ex2_approx((m_run - m_new) * scale_log2e);  // 0 on the first tile
       const float msc = m_new * scale_log2e;
       m_run = m_new;
-      tmem_ld_wait();  // pass-2 chunk 0 has landed in va
+      tmem_ld_wait();
       // ---- fold O_{j-1} into the register accumulator (PV_{j-1} was issued before S_j, so it has completed)
       if (j > 0) {
         const int pj = j - 1;
         mbar_wait(&o_full[pj & 1], (pj >> 1) & 1);
         tc_fence_after();
+        const uint64_t corr2 = pack2(corr, corr);
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           tmem_ld32(tO + lane_base + static_cast<uint32_t>((pj & 1) * 64 + c2 * 32), vb);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c2 * 32 + i] = (acc[c2 * 32 + i] + __uint_as_float(vb[i])) * corr;
+          for (int i = 0; i < 16; ++i)
+            acc[c2 * 16 + i] = mul2(add2(acc[c2 * 16 + i], pack2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]))), corr2);
         }
       }
       // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P into the swizzled smem A-operand tile
-      float l_tile = 0.f;
+      const uint64_t nm2 = pack2(-msc, -msc);
+      uint64_t lsum = 0ull;
       auto emit_p = [&](const uint32_t (&v)[32], int c4) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2e, -msc));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -msc));
-          if (tail) {
+          float x0, x1;
+          unpack2(fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2, nm2), x0, x1);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          if (TAIL) {
             if (kbase + c4 * 32 + i >= ntok) p0 = 0.f;
             if (kbase + c4 * 32 + i + 1 >= ntok) p1 = 0.f;
           }
-          l_tile += p0 + p1;
+          lsum = add2(lsum, pack2(p0, p1));
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         // keys c4*32 .. +31 -> atom (c4 >> 1), 16-byte chunks ((c4 & 1) * 4 + t), t = 0..3
@@ -213,10 +220,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       emit_p(va, 2);
       tmem_ld_wait();
       emit_p(vb, 3);
-      l_run = l_run * corr + l_tile;
+      float l0, l1;
+      unpack2(lsum, l0, l1);
+      l_run = l_run * corr + (l0 + l1);
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();
       mbar_arrive(p_ready);
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j * AT_BN + AT_BN > ntok) softmax_tile(j, std::true_type{});
+      else softmax_tile(j, std::false_type{});
     }
     // ---- last tile's O, normalise, store
     {
@@ -236,7 +252,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           for (int i = 0; i < 32; i += 8) {
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (acc[c2 * 32 + i + e] + __uint_as_float(v[i + e])) * inv;
+            for (int e = 0; e < 8; e += 2) {
+              float a0, a1;
+              unpack2(acc[(c2 * 32 + i + e) >> 1], a0, a1);
+              o[e] = (a0 + __uint_as_float(v[i + e])) * inv;
+              o[e + 1] = (a1 + __uint_as_float(v[i + e + 1])) * inv;
+            }
             *reinterpret_cast<uint4*>(op + c2 * 32 + i) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                            pack_bf16x2(o[6], o[7]));

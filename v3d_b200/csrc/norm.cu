@@ -372,17 +372,19 @@ extern "C" {
  * (diffusionmodules/util.py:259-276, attention.py:130-133, model.py:52-55) and T*H*W for the 3-D
  * time_stack ResBlock (openaimodel.py:267-271 with dims=3: reduction over (C/32, T, H, W)). */
 int v3d_groupnorm_stats(const void* x, void* stats, int64_t rows_per_sample, int32_t nsamples, int32_t C,
-                        int32_t ldx, int32_t groups, void* stream) {
+                        int32_t ldx, int32_t groups, int32_t pre_zeroed, void* stream) {
   if (!x || !stats || C % 8 != 0 || C % groups != 0 || C / 8 > 512 || ldx % 8 != 0 ||
       rows_per_sample <= 0 || nsamples <= 0) {
     set_error("v3d_groupnorm_stats: bad args C=%d groups=%d ldx=%d", C, groups, ldx);
     return V3D_ERR_BAD_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * nsamples, st);
-  if (e != cudaSuccess) {
-    set_error("memset stats: %s", cudaGetErrorString(e));
-    return V3D_ERR_CUDA;
+  if (!pre_zeroed) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * nsamples, st);
+    if (e != cudaSuccess) {
+      set_error("memset stats: %s", cudaGetErrorString(e));
+      return V3D_ERR_CUDA;
+    }
   }
   const int rpc = pick_rows_per_cta(rows_per_sample, nsamples);
   dim3 grid(static_cast<unsigned>((rows_per_sample + rpc - 1) / rpc), nsamples);

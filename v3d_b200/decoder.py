@@ -274,6 +274,8 @@ class VideoDecoder(KernelModule):
         nb = B // T
         P = self.packed()
         dev = z.device
+        n_norms = 4 * sum(1 for n, _, _ in self._blocks() if not n.startswith("@")) + 2
+        object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
         with torch.no_grad():
             cur = torch.empty(B * H * W, zc, device=dev, dtype=torch.bfloat16)
             ops.nchw_f32_to_nhwc_bf16(z.float().contiguous(), cur)
@@ -298,6 +300,7 @@ class VideoDecoder(KernelModule):
             o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
             out = torch.empty(B, self.out_ch, h, w, device=dev, dtype=torch.float32)
             ops.time_mix_conv(o, o.shape[1], P["time_mix.weight"], P["time_mix.bias"], out, nb, T, h * w, self.out_ch)
+            object.__setattr__(self, "_gn_pool", None)
             return out
 
 

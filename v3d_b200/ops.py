@@ -94,12 +94,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
 
 
 def groupnorm_stats(x: torch.Tensor, stats: torch.Tensor, rows_per_sample: int, nsamples: int, c: int,
-                    ldx: Optional[int] = None, groups: int = 32) -> torch.Tensor:
+                    ldx: Optional[int] = None, groups: int = 32, pre_zeroed: bool = False) -> torch.Tensor:
     _need(x, torch.bfloat16, "groupnorm x")
     _need(stats, torch.float64, "groupnorm stats")
     _lib.check(_lib.load().v3d_groupnorm_stats(x.data_ptr(), stats.data_ptr(), rows_per_sample, nsamples, c,
-                                               c if ldx is None else ldx, groups, _stream()),
-               "v3d_groupnorm_stats")
+                                               c if ldx is None else ldx, groups, 1 if pre_zeroed else 0,
+                                               _stream()), "v3d_groupnorm_stats")
     return stats
 
 

@@ -158,9 +158,18 @@ class KernelModule(nn.Module):
 
     def _gn(self, P: dict, key: str, x: torch.Tensor, rows_per_sample: int, nsamples: int, c: int, eps: float,
             silu: bool) -> torch.Tensor:
-        stats = torch.empty(nsamples, 32, 2, device=x.device, dtype=torch.float64)
+        # statistics slices come out of one pool zeroed once per forward (one memset instead of one per norm)
+        pool = getattr(self, "_gn_pool", None)
+        need = nsamples * 64
+        if pool is not None and pool[1] + need <= pool[0].numel():
+            stats = pool[0][pool[1]:pool[1] + need].view(nsamples, 32, 2)
+            pool[1] += need
+            pre_zeroed = True
+        else:
+            stats = torch.empty(nsamples, 32, 2, device=x.device, dtype=torch.float64)
+            pre_zeroed = False
         y = torch.empty(x.shape[0], c, device=x.device, dtype=torch.bfloat16)
-        ops.groupnorm_stats(x, stats, rows_per_sample, nsamples, c)
+        ops.groupnorm_stats(x, stats, rows_per_sample, nsamples, c, pre_zeroed=pre_zeroed)
         ops.groupnorm_apply(x, y, stats, P[key + ".weight"], P[key + ".bias"], rows_per_sample, nsamples, c, eps,
                             silu)
         return y
@@ -767,6 +776,14 @@ class VideoUNet(KernelModule):
         return self._linear(P, nm + ".proj_out", t, rows, out=xn, r1=x, s1=1.0)
 
     def _run(self, P, x, timesteps, ctx2d, y, B, T, nb, H, W, dev):
+        n_norms = sum({"res": 4, "attn": 1, "out": 1}.get(st.kind, 0) for st in self.steps)
+        object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
+        try:
+            return self._run_inner(P, x, timesteps, ctx2d, y, B, T, nb, H, W, dev)
+        finally:
+            object.__setattr__(self, "_gn_pool", None)
+
+    def _run_inner(self, P, x, timesteps, ctx2d, y, B, T, nb, H, W, dev):
         emb_all, cross = self._embeddings(P, timesteps, ctx2d, y, B, T, dev)
         cur = torch.empty(B * H * W, self.in_channels, device=dev, dtype=torch.bfloat16)
         ops.nchw_f32_to_nhwc_bf16(x, cur)
