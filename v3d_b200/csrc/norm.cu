@@ -238,6 +238,95 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16
   }
 }
 
+// LayerNorm, C = LPR * 40 (320 / 640 / 1280): LPR lanes per row, 5 vectors (40 channels) per lane, 32/LPR rows per
+// warp in flight.  Compared with one-warp-per-row this keeps every lane busy at C = 320 (40 vectors), cuts the
+// shuffle reductions to log2(LPR) steps and quadruples the bytes in flight per warp.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+layernorm40_kernel(const bf16* __restrict__ x, const float* __restrict__ add, bf16* __restrict__ ysum,
+                   bf16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   long long rows, int rows_per_frame, float eps) {
+  constexpr int C = LPR * 40;
+  constexpr int RPW = 32 / LPR;  // rows per warp per iteration
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;     // which row of the warp's group
+  const int l = lane % LPR;       // lane within the row
+  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row0 = warp_id * RPW; row0 < rows; row0 += nwarps * RPW) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    float v[5][8];
+    float s = 0.f;
+    if (ok) {
+      const bf16* xr = x + row * C;
+      uint4 u[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xr + (l + i * LPR) * 8));
+      const float* ar = add ? add + (row / rows_per_frame) * C : nullptr;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          v[i][2 * j] = f.x;
+          v[i][2 * j + 1] = f.y;
+        }
+        if (ar) {
+          const int c0 = (l + i * LPR) * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ar + c0)), a1 = __ldg(reinterpret_cast<const float4*>(ar + c0 + 4));
+          v[i][0] += a0.x; v[i][1] += a0.y; v[i][2] += a0.z; v[i][3] += a0.w;
+          v[i][4] += a1.x; v[i][5] += a1.y; v[i][6] += a1.z; v[i][7] += a1.w;
+          if (ysum) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16_rn(v[i][j]));
+            *reinterpret_cast<uint4*>(ysum + row * C + c0) =
+                make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]), pack_bf16x2(v[i][4], v[i][5]),
+                           pack_bf16x2(v[i][6], v[i][7]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / C) + eps);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c0 = (l + i * LPR) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
+        *reinterpret_cast<uint4*>(y + row * C + (l + i * LPR) * 8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // In-place row softmax over bf16 scores (decoder AttnBlock, one 4096-wide row per CTA).
 // ------------------------------------------------------------------------------------------------
@@ -435,6 +524,23 @@ int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const voi
   long long blocks = (rows + warps - 1) / warps;
   const long long cap = 32LL * num_sms();
   if (blocks > cap) blocks = cap;
+  if (C == 320 || C == 640 || C == 1280) {
+    const int lpr = C / 40;
+    const long long rows_per_cta = 8LL * (32 / lpr);
+    long long nb = (rows + rows_per_cta - 1) / rows_per_cta;
+    const long long cap2 = 16LL * num_sms();
+    if (nb > cap2) nb = cap2;
+#define V3D_LN40(L)                                                                                              \
+  layernorm40_kernel<L><<<static_cast<unsigned>(nb), 256, 0, st>>>(                                             \
+      static_cast<const bf16*>(x), static_cast<const float*>(add), static_cast<bf16*>(ysum), static_cast<bf16*>(y), \
+      static_cast<const float*>(gamma), static_cast<const float*>(beta), rows, rows_per_frame > 0 ? rows_per_frame : 1, eps)
+    if (lpr == 8) V3D_LN40(8);
+    else if (lpr == 16) V3D_LN40(16);
+    else V3D_LN40(32);
+#undef V3D_LN40
+    V3D_CHECK_LAUNCH("layernorm40_kernel");
+    return V3D_OK;
+  }
   const int vpl = (C / 8 + 31) / 32;
 #define V3D_LN_LAUNCH(V)                                                                                   \
   layernorm_kernel<V><<<static_cast<unsigned>(blocks), warps * 32, 0, st>>>(                                \
