@@ -194,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
-    uint8_t* stg = staging + (warp - 2) * 4096;
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - 2) * 4096);  // shared-window address
     const int c_begin = half ? CH_HALF : 0;
     const int my_n = half ? NCH - CH_HALF : CH_HALF;
     const bool has_bias = p.bias != nullptr;
@@ -404,11 +404,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           } else {
             // stage this chunk (2 x 16 B) into the warp's slab at 16-byte slots (2kk, 2kk+1) of row `lane`
             const int kk = k & 3;
-            uint8_t* srow = stg + lane * 128;
-            *reinterpret_cast<uint4*>(srow + (((2 * kk) ^ sw) << 4)) =
-                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            *reinterpret_cast<uint4*>(srow + (((2 * kk + 1) ^ sw) << 4)) =
-                make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            const uint32_t srow = stg + static_cast<uint32_t>(lane * 128);
+            sts128(srow + static_cast<uint32_t>(((2 * kk) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            sts128(srow + static_cast<uint32_t>(((2 * kk + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]),
+                   pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
             const int gcol = obase + (c_begin + (k & ~3)) * 16;  // first column of the group being staged
             if (kk == 3) {
               // full group: 8 pieces per row; this lane owns piece (lane & 7) of rows (lane >> 3) + 4 i
@@ -419,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int rr = (lane >> 3) + 4 * i;
                 long long grow;
                 if (map_row(q * 32 + rr, grow)) {
-                  const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                  const uint4 val = lds128(stg + static_cast<uint32_t>(rr * 128 + ((piece ^ (rr & 7)) << 4)));
                   *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
                 }
               }
@@ -433,7 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int piece = idx - rr * ppr;
                 long long grow;
                 if (map_row(q * 32 + rr, grow)) {
-                  const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                  const uint4 val = lds128(stg + static_cast<uint32_t>(rr * 128 + ((piece ^ (rr & 7)) << 4)));
                   *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
                 }
               }
