@@ -271,10 +271,19 @@ def run_native(args) -> None:
     def step_resident():
         return hot_path(x_res.clone(), c_res, uc_res)
 
+    counts = [1] * world  # one image per rank
+    gathered_host = torch.empty(world, T, 8 * L, 8 * L, 3, dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
+
     def step_e2e():
         x, c, uc = upload()
         u8 = hot_path(x, c, uc)
-        frames_host.copy_(u8, non_blocking=True)
+        if world > 1:
+            # the path's only exchange: final decoded-frame gather (uint8 THWC) over NCCL, then D2H on rank 0
+            allf = parallel.gather_frames(u8.unsqueeze(0), counts)
+            if rank == 0:
+                gathered_host.copy_(allf, non_blocking=True)
+        else:
+            frames_host.copy_(u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return frames_host
 
@@ -359,6 +368,13 @@ def run_native(args) -> None:
     breakdown["_probed_step_ms"] = round(probe_ms, 3)
     breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
 
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic_r1.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text())
+        except Exception:
+            traffic = None
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
     n_img = world
@@ -371,15 +387,16 @@ def run_native(args) -> None:
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, "gpu"),
-        "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1000.0 * secs_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": 1000.0 * secs_e2e / args.steps,
+                "api": "DiffusionEngine.sample_views + frames_nchw_to_u8 (+ NCCL frame gather when N > 1)"},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {
             "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / temporal conv / implicit 3x3 conv)",
             "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": (gemm_flops / (gemm_ms * 1e-3) / 1e12) / peak_tf if gemm_ms > 0 else None,
-            "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+            "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
             "launches_per_step": len(records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
             "breakdown_ms_per_step": breakdown,

@@ -169,6 +169,15 @@ if __name__ == "__main__":
         else:
             one_gemm(geglu="nogeglu" not in sys.argv)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "one_conv":
+        n, h, w, ci, co = 36, 64, 64, 320, 320
+        x, wt = bf(n * h * w, ci), bf(co, 9 * ci, scale=(9 * ci) ** -0.5)
+        bias = torch.randn(co, device=DEV)
+        o = torch.empty(n * h * w, co, device=DEV, dtype=torch.bfloat16)
+        for _ in range(6):
+            ops.gemm(x, wt, o, K=ci, N=co, rows_per_batch=n * h * w, bias=bias, conv=(n, h, w))
+        torch.cuda.synchronize()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one_attn":
         qkv = bf(36 * 4096, 960)
         o = torch.empty(36 * 4096, 320, device=DEV, dtype=torch.bfloat16)
