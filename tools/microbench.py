@@ -42,6 +42,9 @@ def bench_gemm(out):
         cases += [(f"L{lvl} qkv", M, C, 3 * C, {}), (f"L{lvl} proj+res", M, C, C, {"res": 1}),
                   (f"L{lvl} geglu", M, C, 8 * C, {"geglu": 1}), (f"L{lvl} ff_out+res", M, 4 * C, C, {"res": 1}),
                   (f"L{lvl} ff_out+blend", M, 4 * C, C, {"res": 2})]
+    if "ksweep" in sys.argv:
+        cases = [(f"ksweep N={n} K={k}", 147456, k, n, o) for n, o in ((960, {}), (320, {"res": 1}), (2560, {"geglu": 1}))
+                 for k in (64, 128, 320, 640, 1280)]
     for name, M, K, N, opt in cases:
         a, w = bf(M, K), bf(N, K, scale=K ** -0.5)
         bias = torch.randn(N, device=DEV)
@@ -185,7 +188,7 @@ if __name__ == "__main__":
             ops.attention_spatial(qkv, o, 36, 4096, 5, 0.125)
         torch.cuda.synchronize()
         sys.exit(0)
-    sel = set(sys.argv[1:]) or {"gemm", "conv", "attn", "norm", "small"}
+    sel = (set(sys.argv[1:]) - {"ksweep"}) or {"gemm", "conv", "attn", "norm", "small"}
     res = []
     if "gemm" in sel:
         bench_gemm(res)

@@ -67,6 +67,28 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   }
 }
 
+// vectorised variant for C % 8 == 0 and Kpad == 9*C: one 16-byte chunk per thread
+__global__ void im2col3x3_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int vpc,
+                                     int stride, int pad, int Ho, int Wo) {
+  const long long total = static_cast<long long>(N) * Ho * Wo * 9 * vpc;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpc);
+    long long p = i / vpc;
+    const int tap = static_cast<int>(p % 9);
+    p /= 9;
+    const int ow = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int oh = static_cast<int>(p % Ho);
+    const long long n = p / Ho;
+    const int ih = oh * stride + tap / 3 - pad;
+    const int iw = ow * stride + tap % 3 - pad;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(&x[((n * H + ih) * W + iw) * vpc + v]);
+    y[i] = val;
+  }
+}
+
 // ---------------- NCHW fp32 -> NHWC bf16 (optional scale), via smem transpose ----------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int C, int HW, float scale) {
   // grid: (ceil(HW/32), N); block 32 x 8. Each block transposes a [C][32-pixel] slab, C in chunks of 32.
@@ -299,6 +321,12 @@ int v3d_im2col3x3(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32
     return V3D_ERR_BAD_ARG;
   }
   const long long total = static_cast<long long>(N) * Hout * Wout * Kpad;
+  if (C % 8 == 0 && Kpad == 9 * C) {
+    im2col3x3_vec_kernel<<<blocks_for(total / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), N, H, W, C / 8, stride, pad, Hout, Wout);
+    V3D_CHECK_LAUNCH("im2col3x3_vec_kernel");
+    return V3D_OK;
+  }
   im2col3x3_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C, stride, pad, Hout, Wout, Kpad);
   V3D_CHECK_LAUNCH("im2col3x3_kernel");

@@ -570,7 +570,35 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     set_error("v3d_gemm_bf16: leading dimensions must be multiples of 8 elements");
     return V3D_ERR_BAD_ARG;
   }
-  const int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, a->act);
+  int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, a->act);
+  if (a->block_n <= 0 && a->act != V3D_ACT_GEGLU && bn >= 128) {
+    // wave quantisation: among the wide tiles that divide N, take the one that fills the SMs best
+    // (e.g. M = 2304, N = 1280: 90 tiles of 128x256 leave 58 SMs idle, 144 tiles of 128x160 do not)
+    long long mt;
+    if (a->conv_w > 0) {
+      const int bw = a->conv_w < BM ? a->conv_w : BM;
+      int bh = BM / bw;
+      if (bh > a->conv_h) bh = a->conv_h;
+      const int bnimg = BM / (bw * (bh > 0 ? bh : 1));
+      mt = static_cast<long long>(a->conv_w / bw) * (a->conv_h / (bh > 0 ? bh : 1)) * ((a->conv_n + bnimg - 1) / bnimg);
+    } else {
+      mt = static_cast<long long>(a->batch > 0 ? a->batch : 1) * ((a->rows_per_batch + BM - 1) / BM);
+    }
+    static const int cands[] = {256, 160, 128};
+    static const double mma_eff[] = {1.0, 0.97, 0.80};  // 128-wide tiles are shared-memory-bandwidth bound
+    double best = -1.0;
+    const int sms = num_sms();
+    for (int i = 0; i < 3; ++i) {
+      if (a->N % cands[i] != 0) continue;
+      const long long tiles = mt * (a->N / cands[i]);
+      const long long waves = (tiles + sms - 1) / sms;
+      const double score = mma_eff[i] * static_cast<double>(tiles) / static_cast<double>(waves * sms);
+      if (score > best + 1e-9) {
+        best = score;
+        bn = cands[i];
+      }
+    }
+  }
   if (bn == 0 || a->N % bn != 0 || (a->act == V3D_ACT_GEGLU && (bn / 2) % 16 != 0)) {
     set_error("v3d_gemm_bf16: no valid N tile for N=%d act=%d block_n=%d", a->N, a->act, a->block_n);
     return V3D_ERR_BAD_ARG;
