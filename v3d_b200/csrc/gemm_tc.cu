@@ -18,7 +18,7 @@ namespace v3d {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kSmemBudget = 225 * 1024;
+constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmEpi {
   void* D;
