@@ -60,7 +60,7 @@ constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-
 template <int BN, bool CONV, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const GemmEpi p) {
+               const __grid_constant__ CUtensorMap mapD, const GemmEpi p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -78,6 +78,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (EPI == EPI_BF16 || EPI == EPI_GEGLU) tma_prefetch_desc(&mapD);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -206,6 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nstore = 0;  // TMA stores issued by this warp (slab ring position)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
@@ -402,43 +404,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int j = 0; j < 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
           } else {
-            // stage this chunk (2 x 16 B) into the warp's slab at 16-byte slots (2kk, 2kk+1) of row `lane`
-            const int kk = k & 3;
-            const uint32_t srow = stg + static_cast<uint32_t>(lane * 128);
-            sts128(srow + static_cast<uint32_t>(((2 * kk) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            sts128(srow + static_cast<uint32_t>(((2 * kk + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]),
-                   pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-            const int gcol = obase + (c_begin + (k & ~3)) * 16;  // first column of the group being staged
-            if (kk == 3) {
-              // full group: 8 pieces per row; this lane owns piece (lane & 7) of rows (lane >> 3) + 4 i
-              __syncwarp();
-              const int piece = lane & 7;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int rr = (lane >> 3) + 4 * i;
-                long long grow;
-                if (map_row(q * 32 + rr, grow)) {
-                  const uint4 val = lds128(stg + static_cast<uint32_t>(rr * 128 + ((piece ^ (rr & 7)) << 4)));
-                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
-                }
-              }
-              __syncwarp();
-            } else if (k + 1 == my_n) {
-              // tail group of (kk+1) chunks: generic mapping
-              __syncwarp();
-              const int ppr = 2 * (kk + 1);
-              for (int idx = lane; idx < 32 * ppr; idx += 32) {
-                const int rr = idx / ppr;
-                const int piece = idx - rr * ppr;
-                long long grow;
-                if (map_row(q * 32 + rr, grow)) {
-                  const uint4 val = lds128(stg + static_cast<uint32_t>(rr * 128 + ((piece ^ (rr & 7)) << 4)));
-                  *reinterpret_cast<uint4*>(static_cast<bf16*>(p.D) + grow * p.ldd + gcol + piece * 8) = val;
-                }
-              }
+            // bf16 rows leave through TMA: the chunk (32 rows x 32 B) is staged in one of the warp's four 1 KB
+            // slabs (dense rows: conflict-free 16-byte stores) and written by one cp.async.bulk.tensor store whose
+            // box is clipped by the hardware at the tensor edge (row tails, image tails).
+            const uint32_t slab = stg + static_cast<uint32_t>((nstore & 3) * 1024);
+            if (nstore >= 4) {
+              if (lane == 0) bulk_wait_read<3>();  // the store issued 4 chunks ago has finished reading this slab
               __syncwarp();
             }
+            sts128(slab + static_cast<uint32_t>(lane * 32), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            sts128(slab + static_cast<uint32_t>(lane * 32 + 16), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                   pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (CONV) {
+                const int tr = q * 32;
+                tma_store_4d(&mapD, slab, obase + c, t0 + (tr & (p.bw - 1)), t1 + ((tr >> p.bw_shift) & (p.bh - 1)),
+                             t2 + (tr >> (p.bw_shift + p.bh_shift)));
+              } else {
+                tma_store_3d(&mapD, slab, obase + c, t1 + q * 32, t0);
+              }
+              bulk_commit();
+            }
+            ++nstore;
           }
         }
       }
@@ -450,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         acc_phase ^= 1u;
       }
     }
+    if (STAGED && lane == 0) bulk_wait_all();  // smem slabs must outlive the last TMA store reads
   }
 
   tc_fence_before();
@@ -474,7 +465,8 @@ static int pick_block_n(int N, int act) {
 }
 
 template <int BN, bool CONV, int EPI>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi, cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmEpi& epi,
+                  cudaStream_t st) {
   using C = Cfg<BN>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, CONV, EPI>;
@@ -488,22 +480,22 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& e
   }
   const int total = epi.num_m_tiles * epi.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, epi);
+  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi);
   V3D_CHECK_LAUNCH("gemm_tc_kernel");
   return V3D_OK;
 }
 
 template <int BN, bool CONV>
-static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
-                        cudaStream_t st) {
+static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                        const GemmEpi& epi, cudaStream_t st) {
   switch (epi_kind) {
-    case EPI_BF16: return launch<BN, CONV, EPI_BF16>(ma, mb, epi, st);
-    case EPI_F32: return launch<BN, CONV, EPI_F32>(ma, mb, epi, st);
+    case EPI_BF16: return launch<BN, CONV, EPI_BF16>(ma, mb, md, epi, st);
+    case EPI_F32: return launch<BN, CONV, EPI_F32>(ma, mb, md, epi, st);
     case EPI_GEGLU:
-      if constexpr (!CONV && (BN / 2) % 16 == 0) return launch<BN, false, EPI_GEGLU>(ma, mb, epi, st);
+      if constexpr (!CONV && (BN / 2) % 16 == 0) return launch<BN, false, EPI_GEGLU>(ma, mb, md, epi, st);
       break;
     case EPI_TRANS:
-      if constexpr (!CONV) return launch<BN, false, EPI_TRANS>(ma, mb, epi, st);
+      if constexpr (!CONV) return launch<BN, false, EPI_TRANS>(ma, mb, md, epi, st);
       break;
   }
   set_error("unsupported epilogue %d for this mode/tile", epi_kind);
@@ -511,15 +503,15 @@ static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& 
 }
 
 template <bool CONV>
-static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const GemmEpi& epi,
-                       cudaStream_t st) {
+static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                       const GemmEpi& epi, cudaStream_t st) {
   switch (bn) {
-    case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, epi, st);
-    case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, epi, st);
-    case 128: return dispatch_epi<128, CONV>(epi_kind, ma, mb, epi, st);
-    case 64: return dispatch_epi<64, CONV>(epi_kind, ma, mb, epi, st);
-    case 32: return dispatch_epi<32, CONV>(epi_kind, ma, mb, epi, st);
-    case 16: return dispatch_epi<16, CONV>(epi_kind, ma, mb, epi, st);
+    case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 128: return dispatch_epi<128, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 64: return dispatch_epi<64, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 32: return dispatch_epi<32, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 16: return dispatch_epi<16, CONV>(epi_kind, ma, mb, md, epi, st);
     default: set_error("unsupported block_n %d", bn); return V3D_ERR_BAD_ARG;
   }
 }
@@ -709,5 +701,26 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     set_error("v3d_gemm_bf16: act=%d is not available with this output mode", a->act);
     return V3D_ERR_UNSUPPORTED;
   }
-  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, e, st) : dispatch_bn<false>(bn, epi_kind, ma, mb, e, st);
+  CUtensorMap md;
+  memset(&md, 0, sizeof(md));
+  if (epi_kind == EPI_BF16 || epi_kind == EPI_GEGLU) {
+    const uint64_t out_cols = static_cast<uint64_t>(e.num_n_tiles) * (epi_kind == EPI_GEGLU ? bn / 2 : bn);
+    if (conv) {
+      const int bw2 = e.bw < 32 ? e.bw : 32;
+      int bh2 = 32 / bw2;
+      if (bh2 > e.bh) bh2 = e.bh;
+      const int bn2 = 32 / (bw2 * bh2);
+      const uint64_t dims[4] = {out_cols, (uint64_t)e.cw, (uint64_t)e.ch, (uint64_t)e.cn};
+      const uint64_t str[3] = {(uint64_t)a->ldd * 2, (uint64_t)a->ldd * 2 * e.cw, (uint64_t)a->ldd * 2 * e.cw * e.ch};
+      const uint32_t box[4] = {16, (uint32_t)bw2, (uint32_t)bh2, (uint32_t)bn2};
+      rc = make_tmap_bf16(&md, a->D, 4, dims, str, box, false);
+    } else {
+      const uint64_t dims[3] = {out_cols, (uint64_t)e.rows_per_batch, (uint64_t)e.batch};
+      const uint64_t str[2] = {(uint64_t)a->ldd * 2, (uint64_t)a->ldd * 2 * e.rows_per_batch};
+      const uint32_t box[3] = {16, 32, 1};
+      rc = make_tmap_bf16(&md, a->D, 3, dims, str, box, false);
+    }
+    if (rc) return rc;
+  }
+  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st) : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st);
 }
