@@ -9,6 +9,8 @@
 // Operand gather modes (see include/v3d_b200.h): linear rows, 3-tap temporal shift, 3x3 spatial taps.
 // The im2row never exists in memory: each (tap, 64-channel) K-block is one TMA box whose out-of-bounds
 // part is zero-filled by the hardware, which is exactly the conv zero padding.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_util.cuh"
 #include "v3d_b200.h"
@@ -31,6 +33,7 @@ struct GemmEpi {
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
   int rows_per_frame, act, out_fp32;
   int b_batched;
+  int dbg;  // diagnostics only (V3D_GEMM_DEBUG): 1 = skip stores, 2 = skip TMA issue, 4 = skip TMEM loads
   int transposed, valid_cols, accumulate;  // small-M mode: D is fp32 [cols][ldd], D[col][row]; bias per row
   // conv3x3 geometry
   int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h, bw_shift, bh_shift;
@@ -295,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr int NBUF = GEGLU ? 1 : 2;
       uint32_t vbuf[NBUF][16];
       uint32_t gbuf[1][16];
-      if (my_n > 0 && !GEGLU) tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
+      if (my_n > 0 && !GEGLU && !(p.dbg & 4)) tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
 #pragma unroll
       for (int k = 0; k < CH_HALF; ++k) {
         if (k < my_n) {
@@ -334,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
           }
-          if (!GEGLU && k + 1 < my_n) tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[GEGLU ? 0 : ((k + 1) & 1)]);
+          if (!GEGLU && k + 1 < my_n && !(p.dbg & 4)) tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[GEGLU ? 0 : ((k + 1) & 1)]);
           if (EPI == EPI_TRANS) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += row_bias;
@@ -408,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // slabs (dense rows: conflict-free 16-byte stores) and written by one cp.async.bulk.tensor store whose
             // box is clipped by the hardware at the tensor edge (row tails, image tails).
             const uint32_t slab = stg + static_cast<uint32_t>((nstore & 3) * 1024);
+            if (p.dbg & 1) continue;
             if (nstore >= 4) {
               if (lane == 0) bulk_wait_read<3>();  // the store issued 4 chunks ago has finished reading this slab
               __syncwarp();
@@ -418,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                    pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & 2)) {
               if (CONV) {
                 const int tr = q * 32;
                 tma_store_4d(&mapD, slab, obase + c, t0 + (tr & (p.bw - 1)), t1 + ((tr >> p.bw_shift) & (p.bh - 1)),
@@ -614,6 +618,14 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   e.rows_per_frame = a->rows_per_frame > 0 ? a->rows_per_frame : 1;
   e.act = a->act;
   e.out_fp32 = a->out_fp32;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* v = getenv("V3D_GEMM_DEBUG");
+      dbg = v ? atoi(v) : 0;
+    }
+    e.dbg = dbg;
+  }
   e.transposed = a->out_transposed;
   e.valid_cols = a->valid_cols > 0 ? a->valid_cols : a->N;
   e.accumulate = a->accumulate;
