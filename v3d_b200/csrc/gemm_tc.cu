@@ -49,8 +49,11 @@ struct Cfg {
   static constexpr int STAGING_BYTES = 8 * 4096;  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled
   static constexpr int NSTAGE_RAW = (kSmemBudget - 2048 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
-  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  // accumulator ring in TMEM: as many stages as fit in the 512 columns (max 4). Deeper rings let the MMA issuer run
+  // further ahead of the epilogue, which hides the tile-to-tile signalling round trip on short-K problems.
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 160 ? 160 : 256)));
+  static constexpr int ACC_STAGES = (512 / ACC_STRIDE) > 4 ? 4 : (512 / ACC_STRIDE);
+  static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -72,8 +75,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::NSTAGE;
   uint64_t* tfull_bar = empty_bar + C::NSTAGE;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
@@ -178,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
         tc_commit(&tfull_bar[acc]);
-        if (++acc == 2) {
+        if (++acc == C::ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1u;
         }
@@ -439,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
+      if (++acc == C::ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;
       }
