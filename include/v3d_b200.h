@@ -92,6 +92,9 @@ int v3d_gemm_bf16(const v3d_gemm_args* args, void* stream);
 int v3d_geglu_pack_rows(int32_t n_out, int32_t block_n, int32_t* perm);
 /* N-tile width the GEMM will choose for a given N (so packers and callers agree). Host function. */
 int v3d_gemm_pick_block_n(int32_t N, int32_t act);
+/* diagnostics only: device buffer (>= 3072 int64) that CTA 0 of subsequent v3d_gemm_bf16 launches fills with per-role
+ * clock64() timelines; NULL disables. */
+int v3d_debug_set_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------
  * Normalisation (norm.cu). GroupNorm is split into a statistics pass and an apply(+SiLU) pass; both

@@ -172,6 +172,31 @@ if __name__ == "__main__":
         else:
             one_gemm(geglu="nogeglu" not in sys.argv)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "trace":
+        from v3d_b200 import _lib
+        M, K, N = [int(a) for a in sys.argv[2:5]]
+        a, w = bf(M, K), bf(N, K, scale=K ** -0.5)
+        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.gemm(a, w, o, K=K, N=N, rows_per_batch=M)
+        buf = torch.zeros(3072, device=DEV, dtype=torch.int64)
+        _lib.load().v3d_debug_set_trace(buf.data_ptr())
+        ops.gemm(a, w, o, K=K, N=N, rows_per_batch=M)
+        torch.cuda.synchronize()
+        _lib.load().v3d_debug_set_trace(None)
+        t = buf.cpu().tolist()
+        P = [x for x in t[:1024] if x]
+        Mm = [x for x in t[1024:2048] if x]
+        E = [x for x in t[2048:] if x]
+        t0 = min(P[0], abs(Mm[0]), E[0])
+        nkb = K // 64
+        print("producer k-block issue times (cycles since start), first 40:", [x - t0 for x in P[:40]])
+        print("mma: tile starts (neg) and k-block full times:", [(-x - t0, 'T') if x < 0 else x - t0 for x in Mm[:60]])
+        print("epilogue warp2 (tfull seen, tile done) pairs:", [(E[i] - t0, E[i + 1] - t0) for i in range(0, min(len(E) - 1, 40), 2)])
+        ntile = len(E) // 2
+        if ntile > 12:
+            print("steady-state cycles per tile (epilogue):", (E[2 * (ntile - 2)] - E[2 * 8]) / (ntile - 2 - 8))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one_conv":
         n, h, w, ci, co = 36, 64, 64, 320, 320
         x, wt = bf(n * h * w, ci), bf(co, 9 * ci, scale=(9 * ci) ** -0.5)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "v3d_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "v3d_geglu_pack_rows": (C.c_int, [_i32, _i32, C.POINTER(C.c_int32)]),
     "v3d_gemm_pick_block_n": (C.c_int, [_i32, _i32]),
+    "v3d_debug_set_trace": (C.c_int, [_vp]),
     # norm.cu
     "v3d_groupnorm_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "v3d_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),

@@ -33,6 +33,7 @@ struct GemmEpi {
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
   int rows_per_frame, act, out_fp32;
   int b_batched;
+  long long* trace;  // diagnostics only: CTA 0 writes role timelines (clock64) here when non-null
   int dbg;  // diagnostics only (V3D_GEMM_DEBUG): 1 = skip stores, 2 = skip TMA issue, 4 = skip TMEM loads
   int transposed, valid_cols, accumulate;  // small-M mode: D is fp32 [cols][ldd], D[col][row]; bias per row
   // conv3x3 geometry
@@ -112,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tr_n = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.num_n_tiles;
         const int m_tile = tile / p.num_n_tiles;
@@ -130,6 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int bz = p.b_batched ? c2 : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (p.trace && blockIdx.x == 0 && tr_n < 1024) p.trace[tr_n++] = clock64();
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -158,13 +161,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int tr_m = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && tr_m < 1020) p.trace[1024 + tr_m++] = -clock64();  // negative: tile start
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (p.trace && blockIdx.x == 0 && tr_m < 1020) p.trace[1024 + tr_m++] = clock64();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + C::A_BYTES);
@@ -214,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t nstore = 0;  // TMA stores issued by this warp (slab ring position)
+    int tr_e = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
@@ -287,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1020) p.trace[2048 + tr_e++] = clock64();
       const uint32_t t_acc =
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -442,6 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1020) p.trace[2048 + tr_e++] = clock64();
       if (++acc == C::ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;
@@ -461,6 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static long long* g_trace = nullptr;  // diagnostics: set through v3d_debug_set_trace
 static int pick_block_n(int N, int act) {
   static const int cands[] = {256, 160, 128, 64, 32, 16};
   for (int c : cands) {
@@ -526,6 +536,13 @@ static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtens
 }  // namespace v3d
 
 using namespace v3d;
+
+/* diagnostics: device buffer of >= 3072 int64 that CTA 0 of every subsequent GEMM launch fills with clock64()
+ * timelines (producer k-blocks | MMA issuer | epilogue warp 2); NULL disables. Not part of the product path. */
+extern "C" int v3d_debug_set_trace(void* buf) {
+  g_trace = static_cast<long long*>(buf);
+  return V3D_OK;
+}
 
 extern "C" int v3d_gemm_pick_block_n(int32_t N, int32_t act) { return pick_block_n(N, act); }
 
@@ -628,6 +645,7 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       dbg = v ? atoi(v) : 0;
     }
     e.dbg = dbg;
+    e.trace = g_trace;
   }
   e.transposed = a->out_transposed;
   e.valid_cols = a->valid_cols > 0 ? a->valid_cols : a->N;
