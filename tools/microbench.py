@@ -3,6 +3,7 @@
 than L2 are cycled so no launch re-reads an L2-resident operand set. Prints one line per shape and a JSON summary.
 Usage: python tools/microbench.py [gemm] [conv] [attn] [norm] [small]"""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -172,6 +173,13 @@ if __name__ == "__main__":
         else:
             one_gemm(geglu="nogeglu" not in sys.argv)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "time":
+        M, K, N = [int(a) for a in sys.argv[2:5]]
+        a, w = bf(M, K), bf(N, K, scale=K ** -0.5)
+        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.gemm(a, w, o, K=K, N=N, rows_per_batch=M))
+        print(f"time M={M} K={K} N={N} dbg={os.environ.get('V3D_GEMM_DEBUG', '0')}: {ms * 1e3:.1f} us  {2 * M * K * N / ms / 1e9:.0f} TF/s")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "trace":
         from v3d_b200 import _lib
         M, K, N = [int(a) for a in sys.argv[2:5]]
@@ -192,10 +200,15 @@ if __name__ == "__main__":
         nkb = K // 64
         print("producer k-block issue times (cycles since start), first 40:", [x - t0 for x in P[:40]])
         print("mma: tile starts (neg) and k-block full times:", [(-x - t0, 'T') if x < 0 else x - t0 for x in Mm[:60]])
-        print("epilogue warp2 (tfull seen, tile done) pairs:", [(E[i] - t0, E[i + 1] - t0) for i in range(0, min(len(E) - 1, 40), 2)])
-        ntile = len(E) // 2
+        # epilogue warp 2 lane 0: per tile [prologue start, acc ready, chunk landed / sub-tile handed to TMA ..., done]
+        per = int(os.environ.get("TRACE_PER", "12"))  # BN=160 group 0: 2 + 6 chunks + 3 sub-tiles + 1
+        ntile = len(E) // per
+        for i in range(min(ntile, 14)):
+            rec = [x - t0 for x in E[i * per:(i + 1) * per]]
+            d = [rec[j + 1] - rec[j] for j in range(per - 1)]
+            print(f"tile {i}: start {rec[0]} deltas {d}")
         if ntile > 12:
-            print("steady-state cycles per tile (epilogue):", (E[2 * (ntile - 2)] - E[2 * 8]) / (ntile - 2 - 8))
+            print("steady-state cycles per tile (epilogue):", (E[per * (ntile - 2)] - E[per * 8]) / (ntile - 2 - 8))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one_conv":
         n, h, w, ci, co = 36, 64, 64, 320, 320

@@ -34,10 +34,12 @@ struct GemmEpi {
   int rows_per_frame, act, out_fp32;
   int b_batched;
   long long* trace;  // diagnostics only: CTA 0 writes role timelines (clock64) here when non-null
-  int dbg;  // diagnostics only (V3D_GEMM_DEBUG): 1 = skip stores, 2 = skip TMA issue, 4 = skip TMEM loads
+  // diagnostics only (V3D_GEMM_DEBUG): 1 = skip the store path, 2 = skip TMA store issue, 4 = skip TMEM loads,
+  // 8 = skip the drain wait, 16 = skip the proxy fence, 32 = skip the smem writes.  Results are wrong with any bit set.
+  int dbg;
   int transposed, valid_cols, accumulate;  // small-M mode: D is fp32 [cols][ldd], D[col][row]; bias per row
   // conv3x3 geometry
-  int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h, bw_shift, bh_shift;
+  int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h, bw_shift, bh_shift, tw_shift, th_shift;  // t*_shift < 0: not pow2
   int num_m_tiles, num_n_tiles;
   float s0, s1, s2;
 };
@@ -59,10 +61,60 @@ struct Cfg {
 };
 
 // epilogue variants (compile-time): what is stored and how
-constexpr int EPI_BF16 = 0;   // bf16 rows through the swizzled smem slab, coalesced stores
+constexpr int EPI_BF16 = 0;   // bf16 sub-tiles staged in shared memory, written by TMA; at most one residual (R1)
+constexpr int EPI_BF16R2 = 4; // as EPI_BF16 with both residuals (blend epilogue); the only variant that carries R2
 constexpr int EPI_GEGLU = 1;  // value * gelu(gate) then as EPI_BF16 (linear mode only)
 constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
+
+// Persistent tile walk without per-tile divisions: tile = blockIdx.x + i * gridDim.x, n fastest.
+struct TileWalk {
+  int n_tile, m_tile, step_n, step_m, num_n;
+  __device__ __forceinline__ explicit TileWalk(const GemmEpi& p) {
+    num_n = p.num_n_tiles;
+    n_tile = static_cast<int>(blockIdx.x) % num_n;
+    m_tile = static_cast<int>(blockIdx.x) / num_n;
+    step_n = static_cast<int>(gridDim.x) % num_n;
+    step_m = static_cast<int>(gridDim.x) / num_n;
+  }
+  __device__ __forceinline__ void next() {
+    n_tile += step_n;
+    m_tile += step_m;
+    if (n_tile >= num_n) {
+      n_tile -= num_n;
+      ++m_tile;
+    }
+  }
+};
+
+// m_tile -> tile origin. conv: (w0, h0, img0); linear: (batch index, first row, 0)
+template <bool CONV>
+__device__ __forceinline__ void tile_origin(const GemmEpi& p, int m_tile, int& t0, int& t1, int& t2) {
+  if (CONV) {
+    int tw, th, tn;
+    if (p.tw_shift >= 0) {
+      tw = m_tile & (p.tiles_w - 1);
+      th = (m_tile >> p.tw_shift) & (p.tiles_h - 1);
+      tn = m_tile >> (p.tw_shift + p.th_shift);
+    } else {
+      tw = m_tile % p.tiles_w;
+      th = (m_tile / p.tiles_w) % p.tiles_h;
+      tn = m_tile / (p.tiles_w * p.tiles_h);
+    }
+    t0 = tw * p.bw;
+    t1 = th * p.bh;
+    t2 = tn * p.bn;
+  } else {
+    if (p.batch == 1) {
+      t0 = 0;
+      t1 = m_tile * BM;
+    } else {
+      t0 = m_tile / p.tiles_per_batch;
+      t1 = (m_tile - t0 * p.tiles_per_batch) * BM;
+    }
+    t2 = 0;
+  }
+}
 
 template <int BN, bool CONV, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -85,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    if (EPI == EPI_BF16 || EPI == EPI_GEGLU) tma_prefetch_desc(&mapD);
+    if (EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU) tma_prefetch_desc(&mapD);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -114,20 +166,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int tr_n = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
-        int c1, c2, c3 = 0;
+      TileWalk tw(p);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next()) {
+        const int n_tile = tw.n_tile;
+        int c1, c2, c3;
         if (CONV) {
-          const int tw = m_tile % p.tiles_w;
-          const int th = (m_tile / p.tiles_w) % p.tiles_h;
-          const int tn = m_tile / (p.tiles_w * p.tiles_h);
-          c1 = tw * p.bw;
-          c2 = th * p.bh;
-          c3 = tn * p.bn;
+          tile_origin<true>(p, tw.m_tile, c1, c2, c3);
         } else {
-          c2 = m_tile / p.tiles_per_batch;
-          c1 = (m_tile % p.tiles_per_batch) * BM;
+          tile_origin<false>(p, tw.m_tile, c2, c1, c3);
         }
         const int bz = p.b_batched ? c2 : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -200,262 +246,283 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // bias/residual loads issued underneath it, math, then either the swizzled smem slab (32 rows x 128 B per
     // warp, flushed as row-contiguous 16-byte stores: 4 full 128-byte lines per warp instruction) or direct fp32.
     constexpr bool GEGLU = EPI == EPI_GEGLU;
-    constexpr bool STAGED = EPI == EPI_BF16 || EPI == EPI_GEGLU;
+    constexpr bool STAGED = EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU;
+    constexpr bool DUAL = EPI == EPI_BF16R2 || EPI == EPI_F32;  // variants that may take a second residual
     constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
     constexpr int NCH = OUT_COLS / 16;
-    constexpr int CH_HALF = (NCH + 1) / 2;
+    // bf16 output leaves as whole-tile-height TMA stores: a sub-tile is 128 rows x SUBW columns, staged by the four
+    // warps of a group (one per TMEM lane quarter) in one of the group's two buffers and written by one
+    // cp.async.bulk.tensor per sub-tile.  Group 0 (warps 2..5) takes the first half of the sub-tiles, group 1 the rest.
+    constexpr int SUBW = (STAGED && OUT_COLS % 32 == 0) ? 32 : 16;
+    constexpr int CPS = SUBW / 16;  // 16-column chunks per sub-tile
+    constexpr int NSUB = OUT_COLS / SUBW;
+    constexpr int CH_HALF = ((NSUB + 1) / 2) * CPS;
+    constexpr int SUB_BYTES = BM * SUBW * 2;
+    static_assert(2 * 2 * SUB_BYTES <= C::STAGING_BYTES, "staging too small");
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
-    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>((warp - 2) * 4096);  // shared-window address
-    const int c_begin = half ? CH_HALF : 0;
-    const int my_n = half ? NCH - CH_HALF : CH_HALF;
+    const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(half * 2 * SUB_BYTES);  // this group's buffers
+    const bool store_leader = q == 0 && lane == 0;
+    const uint32_t row_off = static_cast<uint32_t>(r * SUBW * 2);
+    const uint32_t swz = SUBW == 32 ? static_cast<uint32_t>((r >> 1) & 3) : 0u;  // 64B-swizzle XOR of the 16-byte chunk
     const bool has_bias = p.bias != nullptr;
-    const bool has_fb = p.fbias != nullptr;
-    const bool has_r1 = p.R1 != nullptr;
-    const bool has_r2 = p.R2 != nullptr;
+    // the GEGLU variant carries no residual / per-frame bias code (rejected on the host): registers
+    const bool has_fb = !GEGLU && p.fbias != nullptr;
+    const bool has_r1 = !GEGLU && p.R1 != nullptr;
+    const bool has_r2 = DUAL && p.R2 != nullptr;
     const bool do_silu = p.act == V3D_ACT_SILU;
     const float s0 = p.s0, s1 = p.s1, s2 = p.s2;
-    const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t nstore = 0;  // TMA stores issued by this warp (slab ring position)
+    uint32_t nstore = 0;  // sub-tiles this group has stored (buffer ring position)
     int tr_e = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
-      int t0 = 0, t1 = 0, t2 = 0;
-      if (CONV) {
-        t0 = (m_tile % p.tiles_w) * p.bw;
-        t1 = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
-        t2 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
-      } else {
-        t0 = m_tile / p.tiles_per_batch;
-        t1 = (m_tile % p.tiles_per_batch) * BM;
-      }
+    const bool tracing = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;  // group 0's store leader
+#define V3D_ETRACE() do { if (tracing && tr_e < 1020) p.trace[2048 + tr_e++] = clock64(); } while (0)
+    // TMEM is read in load groups, double-buffered: while one group is processed the next is in flight.  A group is
+    // a whole sub-tile (32 columns, one x32 load) for bf16 output, value+gate (2 x16) for GEGLU, one x16 otherwise.
+    constexpr int LG = GEGLU ? 1 : CPS;          // 16-column output chunks per load group
+    constexpr int LREGS = GEGLU ? 32 : 16 * LG;  // registers per buffer
+    constexpr int NG_HALF = CH_HALF / LG;
+    TileWalk tw(p);
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      V3D_ETRACE();  // [0] tile prologue start
+      const int n_tile = tw.n_tile;
+      int t0, t1, t2;
+      tile_origin<CONV>(p, tw.m_tile, t0, t1, t2);
+      tw.next();  // tw now names the next tile (used by the residual prefetch below)
+      // with an odd number of sub-tiles the two groups swap the larger share every tile, so neither paces the other
+      const int hsel = (NSUB & 1) ? (half ^ (iter & 1)) : half;
+      const int c_begin = hsel ? CH_HALF : 0;
+      const int my_n = hsel ? NCH - CH_HALF : CH_HALF;
+      const int c_begin_next = (NSUB & 1) ? (hsel ? 0 : CH_HALF) : c_begin;
+
+      // accumulator first: the first TMEM load is in flight while the row bookkeeping below is computed
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      V3D_ETRACE();  // [1] accumulator ready
+      const uint32_t t_acc =
+          tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t vb[2][LREGS];
+      auto issue_group = [&](int g, uint32_t* dst) {
+        if (p.dbg & 4) return;
+        const uint32_t c = static_cast<uint32_t>((c_begin + g * LG) * 16);
+        if (GEGLU) {
+          tmem_ld16p(t_acc + c, dst);
+          tmem_ld16p(t_acc + static_cast<uint32_t>(BN / 2) + c, dst + 16);
+        } else if (LG == 2) {
+          tmem_ld32p(t_acc + c, dst);
+        } else {
+          tmem_ld16p(t_acc + c, dst);
+        }
+      };
+      if (my_n > 0) issue_group(0, vb[0]);
+
       // tile row -> (valid, global row). bw/bh are powers of two (checked on the host).
-      auto map_row = [&](int tr, long long& grow) -> bool {
+      auto map_row = [&](int o0, int o1, int o2, long long& grow) -> bool {
         if (CONV) {
-          const int w = tr & (p.bw - 1);
-          const int h = (tr >> p.bw_shift) & (p.bh - 1);
-          const int img = t2 + (tr >> (p.bw_shift + p.bh_shift));
-          grow = (static_cast<long long>(img) * p.ch + (t1 + h)) * p.cw + (t0 + w);
+          const int w = r & (p.bw - 1);
+          const int h = (r >> p.bw_shift) & (p.bh - 1);
+          const int img = o2 + (r >> (p.bw_shift + p.bh_shift));
+          grow = (static_cast<long long>(img) * p.ch + (o1 + h)) * p.cw + (o0 + w);
           return img < p.cn;
         } else {
-          const int m = t1 + tr;
-          grow = static_cast<long long>(t0) * p.rows_per_batch + m;
+          const int m = o1 + r;
+          grow = static_cast<long long>(o0) * p.rows_per_batch + m;
           return m < p.rows_per_batch;
         }
       };
-      long long row;
-      const bool valid = map_row(r, row);
       const int obase = n_tile * OUT_COLS;  // first output column of this tile
       const int nbase = n_tile * BN;        // first column in the (packed) N space
-      const float* fb = (has_fb && valid) ? p.fbias + (row / p.rows_per_frame) * p.ldfb + nbase : nullptr;
-      const bf16* r1p = (has_r1 && valid) ? p.R1 + row * p.ldr1 + obase : nullptr;
-      const bf16* r2p = (has_r2 && valid) ? p.R2 + row * p.ldr2 + obase : nullptr;
+      long long row = 0;
+      bool valid = true;
+      const float* fb = nullptr;
+      const bf16* r1p = nullptr;
+      const bf16* r2p = nullptr;
       float row_bias = 0.f;
-      if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
-      if (has_r1 || has_r2) {
+      if (!STAGED || has_fb || has_r1 || has_r2) {  // plain bf16 tiles never need per-row addresses
+        valid = map_row(t0, t1, t2, row);
+        if (has_fb && valid) fb = p.fbias + static_cast<long long>(static_cast<int>(row) / p.rows_per_frame) * p.ldfb + nbase;
+        if (has_r1 && valid) r1p = p.R1 + row * p.ldr1 + obase;
+        if (has_r2 && valid) r2p = p.R2 + row * p.ldr2 + obase;
+        if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
+      }
+      if ((has_r1 || has_r2) && tile + static_cast<int>(gridDim.x) < total_tiles) {
         // pull the NEXT tile's residual row segments into L2 now; they are consumed one tile-time later
-        const int nt = tile + gridDim.x;
-        if (nt < total_tiles) {
-          const int nn = nt % p.num_n_tiles, nm = nt / p.num_n_tiles;
-          int u0, u1, u2 = 0;
-          if (CONV) {
-            u0 = (nm % p.tiles_w) * p.bw;
-            u1 = ((nm / p.tiles_w) % p.tiles_h) * p.bh;
-            u2 = (nm / (p.tiles_w * p.tiles_h)) * p.bn;
-          } else {
-            u0 = nm / p.tiles_per_batch;
-            u1 = (nm % p.tiles_per_batch) * BM;
-          }
-          long long nrow;
-          bool nvalid;
-          if (CONV) {
-            const int w = r & (p.bw - 1);
-            const int h = (r >> p.bw_shift) & (p.bh - 1);
-            const int img = u2 + (r >> (p.bw_shift + p.bh_shift));
-            nrow = (static_cast<long long>(img) * p.ch + (u1 + h)) * p.cw + (u0 + w);
-            nvalid = img < p.cn;
-          } else {
-            nrow = static_cast<long long>(u0) * p.rows_per_batch + u1 + r;
-            nvalid = u1 + r < p.rows_per_batch;
-          }
-          if (nvalid) {
-            const int ncol0 = nn * OUT_COLS + c_begin * 16;
+        int u0, u1, u2;
+        tile_origin<CONV>(p, tw.m_tile, u0, u1, u2);
+        long long nrow;
+        if (map_row(u0, u1, u2, nrow)) {
+          const int ncol0 = tw.n_tile * OUT_COLS + c_begin_next * 16;
 #pragma unroll
-            for (int off = 0; off < CH_HALF * 16; off += 64) {
-              if (has_r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + nrow * p.ldr1 + ncol0 + off));
-              if (has_r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R2 + nrow * p.ldr2 + ncol0 + off));
-            }
+          for (int off = 0; off < CH_HALF * 16; off += 64) {
+            if (has_r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + nrow * p.ldr1 + ncol0 + off));
+            if (has_r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R2 + nrow * p.ldr2 + ncol0 + off));
           }
         }
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1020) p.trace[2048 + tr_e++] = clock64();
-      const uint32_t t_acc =
-          tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
 
-      // residuals: chunk 0 now, chunk k+1 while chunk k is processed (8 + 8 registers in flight)
-      uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nb0 = na0, nb1 = na0;
-      if (my_n > 0) {
-        if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c_begin * 16) + 1); }
-        if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c_begin * 16) + 1); }
-      }
-      // TMEM accumulator chunks are double-buffered: chunk k+1 is requested as soon as chunk k has landed
-      // (GEGLU tiles load value+gate per chunk without the double buffer: register budget)
-      constexpr int NBUF = GEGLU ? 1 : 2;
-      uint32_t vbuf[NBUF][16];
-      uint32_t gbuf[1][16];
-      if (my_n > 0 && !GEGLU && !(p.dbg & 4)) tmem_ld16(t_acc + static_cast<uint32_t>(c_begin * 16), vbuf[0]);
+      // residuals travel one load group ahead: group g+1's rows are requested before group g is processed, so they
+      // have landed by the time the proxy fence (a full CTA memory barrier) of group g is reached
+      uint4 na[LG][2], nb[LG][2];
 #pragma unroll
-      for (int k = 0; k < CH_HALF; ++k) {
-        if (k < my_n) {
-          const int c = (c_begin + k) * 16;
-          uint32_t (&v)[16] = vbuf[GEGLU ? 0 : (k & 1)];
-          uint32_t (&g)[16] = gbuf[0];
-          if (GEGLU) {
-            tmem_ld16(t_acc + static_cast<uint32_t>(c), v);
-            tmem_ld16(t_acc + static_cast<uint32_t>(BN / 2 + c), g);
-          }
-          // operand loads issued while the TMEM load is in flight
-          float4 bv[4], bg[4], fv[4];
-          const uint4 ra0 = na0, ra1 = na1, rb0 = nb0, rb1 = nb1;
-          if (k + 1 < my_n) {
-            if (r1p) { na0 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16)); na1 = __ldg(reinterpret_cast<const uint4*>(r1p + c + 16) + 1); }
-            if (r2p) { nb0 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16)); nb1 = __ldg(reinterpret_cast<const uint4*>(r2p + c + 16) + 1); }
-          }
-          if (EPI != EPI_TRANS && has_bias) {
+      for (int hh = 0; hh < LG; ++hh) na[hh][0] = na[hh][1] = nb[hh][0] = nb[hh][1] = make_uint4(0, 0, 0, 0);
+      auto load_res = [&](int g) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
-            if (GEGLU) {
+        for (int hh = 0; hh < LG; ++hh) {
+          const int c = (c_begin + g * LG + hh) * 16;
+          if (r1p) { na[hh][0] = __ldg(reinterpret_cast<const uint4*>(r1p + c)); na[hh][1] = __ldg(reinterpret_cast<const uint4*>(r1p + c) + 1); }
+          if (r2p) { nb[hh][0] = __ldg(reinterpret_cast<const uint4*>(r2p + c)); nb[hh][1] = __ldg(reinterpret_cast<const uint4*>(r2p + c) + 1); }
+        }
+      };
+      if (my_n > 0) load_res(0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) bg[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + BN / 2 + c) + j);
-            }
-          }
-          if (fb) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) fv[j] = __ldg(reinterpret_cast<const float4*>(fb + c) + j);
-          }
+      for (int g = 0; g < NG_HALF; ++g) {
+        if (g * LG < my_n) {
           tmem_ld_wait();
-          float f[16];
+          V3D_ETRACE();  // group: TMEM data landed
+          if ((g + 1) * LG < my_n) issue_group(g + 1, vb[(g + 1) & 1]);
+          uint4 ca[LG][2], cb[LG][2];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          float gt[16];
-          if (GEGLU) {
+          for (int hh = 0; hh < LG; ++hh) { ca[hh][0] = na[hh][0]; ca[hh][1] = na[hh][1]; cb[hh][0] = nb[hh][0]; cb[hh][1] = nb[hh][1]; }
+          if ((g + 1) * LG < my_n) load_res(g + 1);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(g[j]);
-          }
-          if (!GEGLU && k + 1 < my_n && !(p.dbg & 4)) tmem_ld16(t_acc + static_cast<uint32_t>(c + 16), vbuf[GEGLU ? 0 : ((k + 1) & 1)]);
-          if (EPI == EPI_TRANS) {
+          for (int hh = 0; hh < LG; ++hh) {
+            const int k = g * LG + hh;
+            const int c = (c_begin + k) * 16;
+            const uint32_t* v = &vb[g & 1][GEGLU ? 0 : hh * 16];
+            const uint32_t* gv = &vb[g & 1][GEGLU ? 16 : 0];
+            const uint4 ra0 = ca[hh][0], ra1 = ca[hh][1], rb0 = cb[hh][0], rb1 = cb[hh][1];
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += row_bias;
-          } else if (has_bias) {
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            // bias vectors are shared by every row: after the first warp touched them they are L1 hits
+            if (EPI == EPI_TRANS) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { f[4 * j] += bv[j].x; f[4 * j + 1] += bv[j].y; f[4 * j + 2] += bv[j].z; f[4 * j + 3] += bv[j].w; }
-          }
-          if (fb) {
+              for (int j = 0; j < 16; ++j) f[j] += row_bias;
+            } else if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { f[4 * j] += fv[j].x; f[4 * j + 1] += fv[j].y; f[4 * j + 2] += fv[j].z; f[4 * j + 3] += fv[j].w; }
-          }
-          if (GEGLU) {
-            if (has_bias) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { gt[4 * j] += bg[j].x; gt[4 * j + 1] += bg[j].y; gt[4 * j + 2] += bg[j].z; gt[4 * j + 3] += bg[j].w; }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_fast(gt[j]);
-          } else if (EPI == EPI_F32 && do_silu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
-          }
-          if (r1p || r2p) {
-            float t[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) t[j] = 0.f;
-            if (r1p) {
-              const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 x2 = unpack_bf16x2(u[j]);
-                t[2 * j] = s1 * x2.x;
-                t[2 * j + 1] = s1 * x2.y;
+              for (int j = 0; j < 4; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
               }
             }
-            if (r2p) {
-              const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
+            if (fb) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 x2 = unpack_bf16x2(u[j]);
-                t[2 * j] = fmaf(s2, x2.x, t[2 * j]);
-                t[2 * j + 1] = fmaf(s2, x2.y, t[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(fb + c) + j);
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
               }
             }
+            if (GEGLU) {
+              float gt[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s0, t[j]);
-          } else if (s0 != 1.0f) {
+              for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(gv[j]);
+              if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] *= s0;
-          }
-          if (EPI == EPI_TRANS) {
-            // D[col][row]: lanes hold consecutive rows -> each store instruction is one contiguous 128-byte line
-            if (valid) {
-              float* dp = static_cast<float*>(p.D) + row;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (obase + c + j < p.valid_cols) {
-                  float* o = dp + static_cast<long long>(obase + c + j) * p.ldd;
-                  *o = p.accumulate ? *o + f[j] : f[j];
+                for (int j = 0; j < 4; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + BN / 2 + c) + j);
+                  gt[4 * j] += b4.x; gt[4 * j + 1] += b4.y; gt[4 * j + 2] += b4.z; gt[4 * j + 3] += b4.w;
                 }
               }
-            }
-          } else if (EPI == EPI_F32) {
-            if (valid) {
-              float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + obase + c);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_fast(gt[j]);
+            } else if (EPI == EPI_F32 && do_silu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
             }
-          } else {
-            // bf16 rows leave through TMA: the chunk (32 rows x 32 B) is staged in one of the warp's four 1 KB
-            // slabs (dense rows: conflict-free 16-byte stores) and written by one cp.async.bulk.tensor store whose
-            // box is clipped by the hardware at the tensor edge (row tails, image tails).
-            const uint32_t slab = stg + static_cast<uint32_t>((nstore & 3) * 1024);
-            if (p.dbg & 1) continue;
-            if (nstore >= 4) {
-              if (lane == 0) bulk_wait_read<3>();  // the store issued 4 chunks ago has finished reading this slab
-              __syncwarp();
-            }
-            sts128(slab + static_cast<uint32_t>(lane * 32), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            sts128(slab + static_cast<uint32_t>(lane * 32 + 16), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                   pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && !(p.dbg & 2)) {
-              if (CONV) {
-                const int tr = q * 32;
-                tma_store_4d(&mapD, slab, obase + c, t0 + (tr & (p.bw - 1)), t1 + ((tr >> p.bw_shift) & (p.bh - 1)),
-                             t2 + (tr >> (p.bw_shift + p.bh_shift)));
-              } else {
-                tma_store_3d(&mapD, slab, obase + c, t1 + q * 32, t0);
+            if (r1p || r2p) {
+              float t[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) t[j] = 0.f;
+              if (r1p) {
+                const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 x2 = unpack_bf16x2(u[j]);
+                  t[2 * j] = s1 * x2.x;
+                  t[2 * j + 1] = s1 * x2.y;
+                }
               }
-              bulk_commit();
+              if (r2p) {
+                const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 x2 = unpack_bf16x2(u[j]);
+                  t[2 * j] = fmaf(s2, x2.x, t[2 * j]);
+                  t[2 * j + 1] = fmaf(s2, x2.y, t[2 * j + 1]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s0, t[j]);
+            } else if (s0 != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] *= s0;
             }
-            ++nstore;
+            if (EPI == EPI_TRANS) {
+              // D[col][row]: lanes hold consecutive rows -> each store instruction is one contiguous 128-byte line
+              if (valid) {
+                float* dp = static_cast<float*>(p.D) + row;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (obase + c + j < p.valid_cols) {
+                    float* o = dp + static_cast<long long>(obase + c + j) * p.ldd;
+                    *o = p.accumulate ? *o + f[j] : f[j];
+                  }
+                }
+              }
+            } else if (EPI == EPI_F32) {
+              if (valid) {
+                float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + row * p.ldd + obase + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
+            } else if (!(p.dbg & 1)) {
+              // bf16 rows leave through TMA.  The chunk goes into this row's slot of the group's current buffer
+              // (64-byte rows, 64B-swizzled: conflict-free 16-byte stores); when the sub-tile is complete the
+              // group meets on its named barrier and one thread issues the 128-row store, which the hardware
+              // clips at the tensor edge (row tails, image tails).
+              const uint32_t buf = stg + static_cast<uint32_t>((nstore & 1) * SUB_BYTES) + row_off;
+              const int part = k % CPS;
+              if (!(p.dbg & 32)) {
+                sts128(buf + (((part * 2) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                       pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                sts128(buf + (((part * 2 + 1) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                       pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+              }
+              if (part == CPS - 1) {
+                if (!(p.dbg & 16)) fence_proxy_async_smem();
+                V3D_ETRACE();  // sub-tile rows written + fenced
+                // the previous store (other buffer) must have drained before anyone refills it after the barrier
+                if (store_leader && !(p.dbg & 8)) bulk_wait_read<0>();
+                V3D_ETRACE();  // previous store drained
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                V3D_ETRACE();  // group met
+                if (store_leader && !(p.dbg & 2)) {
+                  const uint32_t src = stg + static_cast<uint32_t>((nstore & 1) * SUB_BYTES);
+                  const int col0 = obase + c - (CPS - 1) * 16;
+                  if (CONV) tma_store_4d(&mapD, src, col0, t0, t1, t2);
+                  else tma_store_3d(&mapD, src, col0, t1, t0);
+                  bulk_commit();
+                }
+                V3D_ETRACE();  // sub-tile handed to TMA
+                ++nstore;
+              }
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1020) p.trace[2048 + tr_e++] = clock64();
+      V3D_ETRACE();  // tile done
       if (++acc == C::ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
+#undef V3D_ETRACE
     if (STAGED && lane == 0) bulk_wait_all();  // smem slabs must outlive the last TMA store reads
   }
 
@@ -507,6 +574,7 @@ static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& 
                         const GemmEpi& epi, cudaStream_t st) {
   switch (epi_kind) {
     case EPI_BF16: return launch<BN, CONV, EPI_BF16>(ma, mb, md, epi, st);
+    case EPI_BF16R2: return launch<BN, CONV, EPI_BF16R2>(ma, mb, md, epi, st);
     case EPI_F32: return launch<BN, CONV, EPI_F32>(ma, mb, md, epi, st);
     case EPI_GEGLU:
       if constexpr (!CONV && (BN / 2) % 16 == 0) return launch<BN, false, EPI_GEGLU>(ma, mb, md, epi, st);
@@ -575,6 +643,10 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   }
   if (a->out_transposed && (conv || ntaps != 1 || !a->out_fp32 || a->batch > 1 || a->act == V3D_ACT_GEGLU || a->R1 || a->R2 || a->fbias)) {
     set_error("v3d_gemm_bf16: out_transposed needs a plain fp32 linear GEMM (no taps/conv/batch/residual/geglu)");
+    return V3D_ERR_BAD_ARG;
+  }
+  if (a->act == V3D_ACT_GEGLU && (a->R1 || a->R2 || a->fbias)) {
+    set_error("v3d_gemm_bf16: GEGLU takes no residual or per-frame bias");
     return V3D_ERR_BAD_ARG;
   }
   if (!conv && ntaps != 1 && ntaps != 3) {
@@ -685,6 +757,11 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     e.bh_shift = __builtin_ctz(bh);
     e.tiles_w = W / bw;
     e.tiles_h = H / bh;
+    {
+      const bool p2 = (e.tiles_w & (e.tiles_w - 1)) == 0 && (e.tiles_h & (e.tiles_h - 1)) == 0;
+      e.tw_shift = p2 ? __builtin_ctz(e.tiles_w) : -1;
+      e.th_shift = p2 ? __builtin_ctz(e.tiles_h) : -1;
+    }
     e.num_m_tiles = e.tiles_w * e.tiles_h * ((NI + bnimg - 1) / bnimg);
     e.batch = 1; e.rows_per_batch = NI * H * W; e.tiles_per_batch = 1;
     const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
@@ -736,22 +813,26 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   }
   CUtensorMap md;
   memset(&md, 0, sizeof(md));
-  if (epi_kind == EPI_BF16 || epi_kind == EPI_GEGLU) {
+  if (e.R2 != nullptr && e.R1 == nullptr) {  // a lone residual always travels as R1
+    e.R1 = e.R2; e.ldr1 = e.ldr2; e.s1 = e.s2;
+    e.R2 = nullptr;
+  }
+  if (epi_kind == EPI_BF16 && e.R2 != nullptr) epi_kind = EPI_BF16R2;
+  if (epi_kind == EPI_BF16 || epi_kind == EPI_BF16R2 || epi_kind == EPI_GEGLU) {
     const uint64_t out_cols = static_cast<uint64_t>(e.num_n_tiles) * (epi_kind == EPI_GEGLU ? bn / 2 : bn);
+    const uint32_t ocols_tile = epi_kind == EPI_GEGLU ? bn / 2 : bn;
+    const uint32_t subw = ocols_tile % 32 == 0 ? 32 : 16;  // must match SUBW in the kernel
+    const int swz = subw == 32 ? 64 : 0;
     if (conv) {
-      const int bw2 = e.bw < 32 ? e.bw : 32;
-      int bh2 = 32 / bw2;
-      if (bh2 > e.bh) bh2 = e.bh;
-      const int bn2 = 32 / (bw2 * bh2);
       const uint64_t dims[4] = {out_cols, (uint64_t)e.cw, (uint64_t)e.ch, (uint64_t)e.cn};
       const uint64_t str[3] = {(uint64_t)a->ldd * 2, (uint64_t)a->ldd * 2 * e.cw, (uint64_t)a->ldd * 2 * e.cw * e.ch};
-      const uint32_t box[4] = {16, (uint32_t)bw2, (uint32_t)bh2, (uint32_t)bn2};
-      rc = make_tmap_bf16(&md, a->D, 4, dims, str, box, false);
+      const uint32_t box[4] = {subw, (uint32_t)e.bw, (uint32_t)e.bh, (uint32_t)e.bn};
+      rc = make_tmap_bf16(&md, a->D, 4, dims, str, box, swz);
     } else {
       const uint64_t dims[3] = {out_cols, (uint64_t)e.rows_per_batch, (uint64_t)e.batch};
       const uint64_t str[2] = {(uint64_t)a->ldd * 2, (uint64_t)a->ldd * 2 * e.rows_per_batch};
-      const uint32_t box[3] = {16, 32, 1};
-      rc = make_tmap_bf16(&md, a->D, 3, dims, str, box, false);
+      const uint32_t box[3] = {subw, BM, 1};
+      rc = make_tmap_bf16(&md, a->D, 3, dims, str, box, swz);
     }
     if (rc) return rc;
   }

@@ -49,7 +49,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -71,7 +71,10 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                         : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -17,10 +17,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
-// bf16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides[i] is the byte
-// stride of dim i+1. Returns 0 on success.
+// bf16 tensor map, zero OOB fill. dims/strides innermost first; strides[i] is the byte stride of dim i+1.
+// swizzle_bytes: 128 / 64 / 32, or 0 for a dense box. Returns 0 on success.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 #define V3D_CHECK_LAUNCH(name)                                            \
   do {                                                                    \
