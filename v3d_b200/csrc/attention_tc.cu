@@ -1,15 +1,19 @@
 // Spatial self-attention on the 5th-gen tensor cores (head dim 64, bf16 operands, fp32 softmax).
 //
-// One CTA = one (sample, head) x 128 queries; it streams 128-key K/V tiles:
-//   warp 0      : TMA producer (Q once; K_j, V_j through a 2-stage mbarrier ring, 128B swizzle)
+// One CTA = one (sample, head) x 128 queries; it streams 64-key K/V tiles:
+//   warp 0      : TMA producer (Q once; K_j, V_j through a 3-stage mbarrier ring, 128B swizzle)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//                   S_j = Q K_j^T      (128x128x64,  A,B K-major)          -> TMEM cols [0,128)
-//                   O_j = P_j V_j      (128x64x128,  A = P K-major in smem, B = V MN-major) -> TMEM cols 128+64*(j&1)
-//   warps 2..5  : softmax: thread r owns query row r = its TMEM lane.  Two passes over the S row straight from
-//                 TMEM (row max, then exp2 / row sum), P written as bf16 into the swizzled smem operand tile,
-//                 O_{j-1} pulled from TMEM and folded into a register accumulator with the running-max correction.
-// TMEM per CTA: 256 columns; shared memory ~112 KB -> two CTAs per SM interleave (one in softmax while the
-// other's MMAs run), which is what hides the single-CTA S -> softmax -> PV dependency chain.
+//                   S_j = Q K_j^T   (128x64x64, A,B K-major)                       -> TMEM S[j&1] (2 x 64 columns)
+//                   O  += P_j V_j   (128x64x64, A = P K-major in smem, B = V MN-major) -> TMEM O (64 columns)
+//                 S_{j+1} is issued BEFORE P_j V_j, so the next scores are ready when the softmax warps come back.
+//   warps 2..5  : softmax: thread r owns query row r = its TMEM lane.  The 64 scores of the tile are pulled into
+//                 registers once (the S buffer is released immediately), row max, exp2, row sum, bf16 P into the
+//                 swizzled smem operand tile P[j&1].
+// O stays in TMEM for the whole key loop.  The softmax runs against a lagged row maximum: the reference point only
+// moves when the tile maximum exceeds it by more than 2^8 (then the warp rescales its O rows in TMEM and the running
+// sum); otherwise P is simply up to 256x larger, which fp32 sums and bf16 P hold without loss.  Mathematically the
+// result is the exact softmax; only rounding differs.
+// TMEM per CTA: 256 columns; shared memory ~97 KB -> two CTAs per SM.
 #include <type_traits>
 
 #include "common.cuh"
@@ -19,16 +23,19 @@
 namespace v3d {
 
 constexpr int AT_BM = 128;
-constexpr int AT_BN = 128;
+constexpr int AT_BN = 64;
 constexpr int AT_THREADS = 192;
-constexpr int AT_TILE = 128 * 128;                 // bytes of a [128][64] bf16 tile
+constexpr int AT_KVSTAGES = 3;
+constexpr int AT_QTILE = 128 * 128;                // bytes of a [128][64] bf16 tile (Q, P)
+constexpr int AT_KTILE = 64 * 128;                 // bytes of a [64][64] bf16 tile (K, V)
 constexpr int AT_OFF_Q = 0;
-constexpr int AT_OFF_K = AT_OFF_Q + AT_TILE;       // 2 stages
-constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_TILE;   // 2 stages
-constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_TILE;   // 2 atoms of 64 keys
-constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_TILE;
+constexpr int AT_OFF_K = AT_OFF_Q + AT_QTILE;
+constexpr int AT_OFF_V = AT_OFF_K + AT_KVSTAGES * AT_KTILE;
+constexpr int AT_OFF_P = AT_OFF_V + AT_KVSTAGES * AT_KTILE;  // 2 buffers
+constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_QTILE;
 constexpr int AT_SMEM = AT_OFF_BAR + 256;
 constexpr uint32_t AT_TMEM_COLS = 256;
+constexpr float AT_RESCALE_LOG2 = 8.0f;            // move the softmax reference only for a > 2^8 overshoot
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -38,12 +45,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   uint8_t* smem = at_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* o_full = bars + 7;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* s_empty = bars + 9;    // [2]  128 arrivals: every softmax thread has its scores in registers
+  uint64_t* p_ready = bars + 11;   // [2]  128 arrivals
+  uint64_t* pv_done = bars + 13;   // [2]  P_j V_j retired (P[j&1] reusable, O readable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BM;
@@ -57,13 +65,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < AT_KVSTAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-      mbar_init(&o_full[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -74,170 +85,172 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;            // 128 columns
-  const uint32_t tO = tmem_base + 128;      // 2 x 64 columns
+  const uint32_t tS = tmem_base;            // 2 x 64 columns
+  const uint32_t tO = tmem_base + 128;      // 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE);
+      mbar_arrive_expect_tx(q_full, AT_QTILE);
       tma_load_3d(smem + AT_OFF_Q, &mapQ, q_full, head * 64, q0, b);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
-        tma_load_3d(smem + AT_OFF_K + st * AT_TILE, &mapK, &kv_full[st], head * 64, j * AT_BN, b);
-        tma_load_3d(smem + AT_OFF_V + st * AT_TILE, &mapV, &kv_full[st], head * 64, j * AT_BN, b);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * AT_KTILE);
+        tma_load_3d(smem + AT_OFF_K + st * AT_KTILE, &mapK, &kv_full[st], head * 64, j * AT_BN, b);
+        tma_load_3d(smem + AT_OFF_V + st * AT_KTILE, &mapV, &kv_full[st], head * 64, j * AT_BN, b);
+        if (++st == AT_KVSTAGES) {
+          st = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major: d contiguous
       const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + AT_OFF_Q));
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + st * AT_TILE));
+      auto issue_s = [&](int j, int st) {
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + AT_OFF_K + st * AT_KTILE));
+        const uint32_t d_s = tS + static_cast<uint32_t>((j & 1) * 64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tS, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
-        tc_commit(s_full);
-        mbar_wait(p_ready, j & 1);
-        tc_fence_after();
-        const uint32_t vbase = smem_u32(smem + AT_OFF_V + st * AT_TILE);
-        const uint32_t d_o = tO + static_cast<uint32_t>((j & 1) * 64);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t dp = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P + (kk >> 2) * AT_TILE)) +
-                              static_cast<uint64_t>(2 * (kk & 3));
-          const uint64_t dv = umma_desc_mn_sw128(vbase + kk * 2048, AT_TILE);
-          tc_mma_f16(d_o, dp, dv, idesc_pv, kk != 0);
+          tc_mma_f16(d_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
+        tc_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      int st = 0;       // ring stage of tile j
+      uint32_t ph = 0;  // its phase
+      for (int j = 0; j < nkv; ++j) {
+        int st1 = st + 1;
+        uint32_t ph1 = ph;
+        if (st1 == AT_KVSTAGES) {
+          st1 = 0;
+          ph1 ^= 1u;
         }
-        tc_commit(&o_full[j & 1]);
+        if (j + 1 < nkv) {
+          mbar_wait(&kv_full[st1], ph1);
+          mbar_wait(&s_empty[(j + 1) & 1], (((j + 1) >> 1) & 1) ^ 1u);  // softmax j-1 holds its scores in registers
+          tc_fence_after();
+          issue_s(j + 1, st1);
+        }
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(smem + AT_OFF_V + st * AT_KTILE);
+        const uint64_t dp0 = umma_desc_k_sw128(smem_u32(smem + AT_OFF_P + (j & 1) * AT_QTILE));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t dv = umma_desc_mn_sw128(vbase + kk * 2048, AT_KTILE);
+          tc_mma_f16(tO, dp0 + static_cast<uint64_t>(2 * kk), dv, idesc_pv, (j | kk) != 0);
+        }
+        tc_commit(&pv_done[j & 1]);
         tc_commit(&kv_empty[st]);
+        st = st1;
+        ph = ph1;
       }
     }
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    uint8_t* prow = smem + AT_OFF_P + r * 128;
     const int sw = r & 7;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint64_t acc[32];  // O accumulator, 64 fp32 as 32 packed pairs (FFMA2/FADD2/FMUL2 halve the issue slots)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0ull;
+    float m_ref = -INFINITY, l_run = 0.f;
     const uint64_t sl2 = pack2(scale_log2e, scale_log2e);
 
-    // One 128-key tile. TAIL = the tile crosses ntok: keys beyond it are masked (only the last tile can be one).
+    // One 64-key tile. TAIL = the tile crosses ntok: keys beyond it are masked (only the last tile can be one).
     auto softmax_tile = [&](int j, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
       const int kbase = j * AT_BN;
-      uint32_t va[32], vb[32];  // double-buffered TMEM chunks
-      // ---- pass 1: row max (FMNMX3: two elements per instruction)
+      const int sb = j & 1;
+      uint32_t s[64];
+      tmem_ld32p(tS + lane_base + static_cast<uint32_t>(sb * 64), s);
+      tmem_ld32p(tS + lane_base + static_cast<uint32_t>(sb * 64 + 32), s + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);  // the scores live in registers now: S[sb] may take tile j+2
+      // ---- row max (FMNMX3: two elements per instruction)
       float mx = -INFINITY;
-      auto scan_max = [&](const uint32_t (&v)[32], int c4) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]);
-          if (TAIL) {
-            if (kbase + c4 * 32 + i >= ntok) a0 = -INFINITY;
-            if (kbase + c4 * 32 + i + 1 >= ntok) a1 = -INFINITY;
-          }
-          mx = fmaxf(fmaxf(a0, a1), mx);
+      for (int i = 0; i < 64; i += 2) {
+        float a0 = __uint_as_float(s[i]), a1 = __uint_as_float(s[i + 1]);
+        if (TAIL) {
+          if (kbase + i >= ntok) a0 = -INFINITY;
+          if (kbase + i + 1 >= ntok) a1 = -INFINITY;
         }
-      };
-      tmem_ld32(tS + lane_base, va);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base + 32u, vb);
-      scan_max(va, 0);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base + 64u, va);
-      scan_max(vb, 1);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base + 96u, vb);
-      scan_max(va, 2);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base, va);  // first chunk of pass 2, requested while the last max chunk is reduced
-      scan_max(vb, 3);
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = ex2_approx((m_run - m_new) * scale_log2e);  // 0 on the first tile
-      const float msc = m_new * scale_log2e;
-      m_run = m_new;
-      tmem_ld_wait();
-      // ---- fold O_{j-1} into the register accumulator (PV_{j-1} was issued before S_j, so it has completed)
-      if (j > 0) {
-        const int pj = j - 1;
-        mbar_wait(&o_full[pj & 1], (pj >> 1) & 1);
-        tc_fence_after();
-        const uint64_t corr2 = pack2(corr, corr);
+        mx = fmaxf(fmaxf(a0, a1), mx);
+      }
+      if (j == 0) {
+        m_ref = mx;  // nothing accumulated yet
+      } else {
+        const bool need = (mx - m_ref) * scale_log2e > AT_RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          // move the reference for the rows that overshot: O rows and the running sum shrink by 2^(old - new)
+          float fac = 1.0f;
+          if (need) {
+            fac = ex2_approx((m_ref - mx) * scale_log2e);
+            m_ref = mx;
+          }
+          l_run *= fac;
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // O holds tiles 0..j-1
+          tc_fence_after();
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          tmem_ld32(tO + lane_base + static_cast<uint32_t>((pj & 1) * 64 + c2 * 32), vb);
-          tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld16p(tO + lane_base + static_cast<uint32_t>(c * 16), o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            acc[c2 * 16 + i] = mul2(add2(acc[c2 * 16 + i], pack2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]))), corr2);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * fac);
+            tmem_st16p(tO + lane_base + static_cast<uint32_t>(c * 16), o);
+          }
+          tmem_st_wait();
         }
       }
-      // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P into the swizzled smem A-operand tile
+      // P[sb] was last read by P_{j-2} V_{j-2}
+      if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+      // ---- P = exp2(s*scale - m_ref*scale), row sum, bf16 P into the swizzled smem A-operand tile
+      const float msc = m_ref * scale_log2e;
       const uint64_t nm2 = pack2(-msc, -msc);
       uint64_t lsum = 0ull;
-      auto emit_p = [&](const uint32_t (&v)[32], int c4) {
-        uint32_t pk[16];
+      uint8_t* prow = smem + AT_OFF_P + sb * AT_QTILE + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
+      for (int c = 0; c < 8; ++c) {  // 8 keys -> one 16-byte chunk
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const int i = c * 8 + e;
           float x0, x1;
-          unpack2(fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2, nm2), x0, x1);
+          unpack2(fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sl2, nm2), x0, x1);
           float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
           if (TAIL) {
-            if (kbase + c4 * 32 + i >= ntok) p0 = 0.f;
-            if (kbase + c4 * 32 + i + 1 >= ntok) p1 = 0.f;
+            if (kbase + i >= ntok) p0 = 0.f;
+            if (kbase + i + 1 >= ntok) p1 = 0.f;
           }
           lsum = add2(lsum, pack2(p0, p1));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[e >> 1] = pack_bf16x2(p0, p1);
         }
-        // keys c4*32 .. +31 -> atom (c4 >> 1), 16-byte chunks ((c4 & 1) * 4 + t), t = 0..3
-        uint8_t* pa = prow + (c4 >> 1) * AT_TILE;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int chunk = (c4 & 1) * 4 + t;
-          *reinterpret_cast<uint4*>(pa + ((chunk ^ sw) << 4)) =
-              make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        }
-      };
-      tmem_ld32(tS + lane_base + 32u, vb);
-      emit_p(va, 0);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base + 64u, va);
-      emit_p(vb, 1);
-      tmem_ld_wait();
-      tmem_ld32(tS + lane_base + 96u, vb);
-      emit_p(va, 2);
-      tmem_ld_wait();
-      emit_p(vb, 3);
+        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
       float l0, l1;
       unpack2(lsum, l0, l1);
-      l_run = l_run * corr + (l0 + l1);
+      l_run += l0 + l1;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[sb]);
     };
 
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       if (j * AT_BN + AT_BN > ntok) softmax_tile(j, std::true_type{});
       else softmax_tile(j, std::false_type{});
     }
-    // ---- last tile's O, normalise, store
+    // ---- O is complete after the last P V: normalise, store
     {
       const int pj = nkv - 1;
-      mbar_wait(&o_full[pj & 1], (pj >> 1) & 1);
+      mbar_wait(&pv_done[pj & 1], (pj >> 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
       const int row = q0 + r;
@@ -245,22 +258,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         uint32_t v[32];
-        tmem_ld32(tO + lane_base + static_cast<uint32_t>((pj & 1) * 64 + c2 * 32), v);
+        tmem_ld32p(tO + lane_base + static_cast<uint32_t>(c2 * 32), v);
         tmem_ld_wait();
         if (row < ntok) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            float o[8];
+            uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              float a0, a1;
-              unpack2(acc[(c2 * 32 + i + e) >> 1], a0, a1);
-              o[e] = (a0 + __uint_as_float(v[i + e])) * inv;
-              o[e + 1] = (a1 + __uint_as_float(v[i + e + 1])) * inv;
-            }
-            *reinterpret_cast<uint4*>(op + c2 * 32 + i) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                           pack_bf16x2(o[6], o[7]));
+            for (int e = 0; e < 8; e += 2)
+              w[e >> 1] = pack_bf16x2(__uint_as_float(v[i + e]) * inv, __uint_as_float(v[i + e + 1]) * inv);
+            *reinterpret_cast<uint4*>(op + c2 * 32 + i) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
@@ -295,11 +302,12 @@ int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, 
   const uint64_t dims[3] = {static_cast<uint64_t>(nheads) * 64, static_cast<uint64_t>(ntok),
                             static_cast<uint64_t>(nbatch)};
   const uint64_t str[2] = {static_cast<uint64_t>(ld_qkv) * 2, static_cast<uint64_t>(ld_qkv) * 2 * ntok};
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box_q[3] = {64, AT_BM, 1};
+  const uint32_t box_kv[3] = {64, AT_BN, 1};
   int rc;
-  if ((rc = make_tmap_bf16(&mq, q, 3, dims, str, box))) return rc;
-  if ((rc = make_tmap_bf16(&mk, k, 3, dims, str, box))) return rc;
-  if ((rc = make_tmap_bf16(&mv, v, 3, dims, str, box))) return rc;
+  if ((rc = make_tmap_bf16(&mq, q, 3, dims, str, box_q))) return rc;
+  if ((rc = make_tmap_bf16(&mk, k, 3, dims, str, box_kv))) return rc;
+  if ((rc = make_tmap_bf16(&mv, v, 3, dims, str, box_kv))) return rc;
   static bool cfg = false;
   if (!cfg) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
