@@ -321,6 +321,7 @@ def run_native(args) -> None:
     #      by CUDA events on the launching stream (a separate pass, so the timed region above carries no probes)
     records = []      # (flops, e0, e1) for tensor-core GEMM/conv launches
     families = {}     # op name -> list of (e0, e1)
+    shapes = {}       # GEMM shape key -> list of (flops, e0, e1)
     host_only = {"launch_count", "pick_block_n", "geglu_perm"}
     saved = {}
 
@@ -336,6 +337,11 @@ def run_native(args) -> None:
                 rows = kw["rows_per_batch"] * kw.get("batch", 1)
                 taps = 9 if kw.get("conv") is not None else kw.get("ntaps", 1)
                 records.append((2.0 * rows * N * K * taps, e0, e1))
+                skey = "%s M=%d K=%d N=%d%s%s%s%s" % (
+                    "conv3x3" if kw.get("conv") is not None else ("tconv" if taps == 3 else "linear"), rows, K, N,
+                    " geglu" if kw.get("act", 0) == ops.ACT_GEGLU else "", " +R1" if kw.get("r1") is not None else "",
+                    " +R2" if kw.get("r2") is not None else "", " f32" if kw.get("out_fp32") else "")
+                shapes.setdefault(skey, []).append((2.0 * rows * N * K * taps, e0, e1))
                 fam = "gemm.conv3x3" if kw.get("conv") is not None else ("gemm.temporal" if taps == 3 else "gemm.linear")
             families.setdefault(fam, []).append((e0, e1))
             return r
@@ -365,6 +371,13 @@ def run_native(args) -> None:
     probe_ms = pe0.elapsed_time(pe1)
     breakdown = {k: {"ms": round(sum(a.elapsed_time(b) for a, b in v), 3), "launches": len(v)}
                  for k, v in sorted(families.items())}
+    shape_rows = []
+    for k, v in shapes.items():
+        ms = sum(a.elapsed_time(b) for _, a, b in v)
+        fl = sum(f for f, _, _ in v)
+        shape_rows.append({"shape": k, "launches": len(v), "ms": round(ms, 3),
+                           "tflops": round(fl / ms / 1e9, 1) if ms > 0 else None})
+    shape_rows.sort(key=lambda r: -r["ms"])
     breakdown["_probed_step_ms"] = round(probe_ms, 3)
     breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
 
@@ -400,6 +413,7 @@ def run_native(args) -> None:
             "launches_per_step": len(records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
             "breakdown_ms_per_step": breakdown,
+            "gemm_shapes_top": shape_rows[:30],
             "model": {"reference_accounting_tflop_per_step": model_tf,
                       "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
         },

@@ -160,6 +160,8 @@ def one_gemm(M=147456, K=320, N=2560, geglu=True, iters=6):
     kw = dict(K=K, N=N, rows_per_batch=M, bias=bias)
     if geglu:
         kw["act"] = ops.ACT_GEGLU
+    if "res" in sys.argv:
+        kw.update(r1=bf(M, N), s1=1.0)
     for _ in range(iters):
         ops.gemm(a, w, o, **kw)
     torch.cuda.synchronize()

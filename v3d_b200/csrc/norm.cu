@@ -1,6 +1,8 @@
 // Memory-bound normalisation kernels on NHWC / token-major bf16 activations (fp32 statistics):
 // GroupNorm(32) statistics + apply(+SiLU), LayerNorm (+ fused per-frame add), row softmax.
 // All global accesses are 16-byte vectors along the contiguous channel dimension.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_util.cuh"
 #include "v3d_b200.h"
@@ -12,7 +14,7 @@ namespace v3d {
 // grid = (row chunks, samples); each thread owns one 8-channel vector column and strides over rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
-constexpr int kGnUnroll = 4;  // independent 16-byte loads in flight per thread
+constexpr int kGnUnroll = 8;  // independent 16-byte loads in flight per thread
 
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats, long long rows_per_sample,
@@ -440,8 +442,15 @@ softmax_rows_f32_kernel(const float* __restrict__ x, bf16* __restrict__ y, int n
 }
 
 static int pick_rows_per_cta(long long rows_per_sample, int nsamples) {
-  // aim for >= ~8 waves of CTAs over the SMs while keeping at least 32 rows per CTA
-  const long long target = 8LL * num_sms();
+  // a few CTAs per SM, each with enough rows that the per-CTA prologue / reduction tail stays small next to the
+  // streaming loop (V3D_GN_WAVES overrides the CTA-per-SM target: tuning knob)
+  static int waves = 0;
+  if (waves == 0) {
+    const char* v = getenv("V3D_GN_WAVES");
+    waves = v ? atoi(v) : 4;
+    if (waves < 1) waves = 1;
+  }
+  const long long target = static_cast<long long>(waves) * num_sms();
   long long chunks = (target + nsamples - 1) / nsamples;
   if (chunks < 1) chunks = 1;
   long long rpc = (rows_per_sample + chunks - 1) / chunks;
