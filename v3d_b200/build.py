@@ -28,6 +28,9 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-I", str(INCLUDE), "-I", str(CSRC),
 ]
+# V3D_GEMM_DIAG=1 builds the GEMM with its diagnostics (role timelines, stage-skipping switches) compiled in
+if os.environ.get("V3D_GEMM_DIAG"):
+    NVCC_FLAGS.append("-DV3D_GEMM_DIAG")
 
 
 def _nvcc() -> str:

@@ -316,6 +316,14 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// 16-byte read-only load that does not allocate in L1 (data consumed once)
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -345,6 +353,18 @@ __device__ __forceinline__ float gelu_phi_fast(float x) {
   return fmaf(tanh_approx(x * p), 0.5f, 0.5f);  // Phi(x)
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) { return x * gelu_phi_fast(x); }
+// the same function on a packed pair: 6 packed FP32 ops + 2 MUFU for two elements
+__device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x) {
+  const uint64_t xx = mul2(x, x);
+  uint64_t p = fma2(xx, pack2(-0.00035151753388801277f, -0.00035151753388801277f),
+                    pack2(0.03700565095560008f, 0.03700565095560008f));
+  p = fma2(xx, p, pack2(0.7975078784258718f, 0.7975078784258718f));
+  float a, b;
+  unpack2(mul2(x, p), a, b);
+  const uint64_t phi = fma2(pack2(tanh_approx(a), tanh_approx(b)), pack2(0.5f, 0.5f), pack2(0.5f, 0.5f));
+  return mul2(x, phi);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

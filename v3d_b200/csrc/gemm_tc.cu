@@ -44,6 +44,16 @@ struct GemmEpi {
   float s0, s1, s2;
 };
 
+// Diagnostics (role timelines through v3d_debug_set_trace, V3D_GEMM_DEBUG stage-skipping switches) are compiled in
+// only with -DV3D_GEMM_DIAG: the hooks cost registers and ~6% of the epilogue's issue slots.
+#ifdef V3D_GEMM_DIAG
+#define V3D_DIAG(x) (x)
+#define V3D_DBG(bit) (p.dbg & (bit))
+#else
+#define V3D_DIAG(x) (false)
+#define V3D_DBG(bit) (0)
+#endif
+
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -178,7 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int bz = p.b_batched ? c2 : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (p.trace && blockIdx.x == 0 && tr_n < 1024) p.trace[tr_n++] = clock64();
+          if (V3D_DIAG(p.trace && blockIdx.x == 0 && tr_n < 1024)) p.trace[tr_n++] = clock64();
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -211,12 +221,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        if (p.trace && blockIdx.x == 0 && tr_m < 1020) p.trace[1024 + tr_m++] = -clock64();  // negative: tile start
+        if (V3D_DIAG(p.trace && blockIdx.x == 0 && tr_m < 1020)) p.trace[1024 + tr_m++] = -clock64();  // negative: tile start
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (p.trace && blockIdx.x == 0 && tr_m < 1020) p.trace[1024 + tr_m++] = clock64();
+          if (V3D_DIAG(p.trace && blockIdx.x == 0 && tr_m < 1020)) p.trace[1024 + tr_m++] = clock64();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + C::A_BYTES);
@@ -277,8 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t acc_phase = 0;
     uint32_t nstore = 0;  // sub-tiles this group has stored (buffer ring position)
     int tr_e = 0;
-    const bool tracing = p.trace && blockIdx.x == 0 && warp == 4 && lane == 0;  // group 0's store leader
-#define V3D_ETRACE() do { if (tracing && tr_e < 1020) p.trace[2048 + tr_e++] = clock64(); } while (0)
+    const bool tracing = V3D_DIAG(p.trace && blockIdx.x == 0 && warp == 4 && lane == 0);  // group 0's store leader
+#define V3D_ETRACE() do { if (V3D_DIAG(tracing && tr_e < 1020)) p.trace[2048 + tr_e++] = clock64(); } while (0)
     // TMEM is read in load groups, double-buffered: while one group is processed the next is in flight.  A group is
     // a whole sub-tile (32 columns, one x32 load) for bf16 output, value+gate (2 x16) for GEGLU, one x16 otherwise.
     constexpr int LG = GEGLU ? 1 : CPS;          // 16-column output chunks per load group
@@ -306,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tmem_base + static_cast<uint32_t>(acc * C::ACC_STRIDE) + (static_cast<uint32_t>(q * 32) << 16);
       uint32_t vb[2][LREGS];
       auto issue_group = [&](int g, uint32_t* dst) {
-        if (p.dbg & 4) return;
+        if (V3D_DBG(4)) return;
         const uint32_t c = static_cast<uint32_t>((c_begin + g * LG) * 16);
         if (GEGLU) {
           tmem_ld16p(t_acc + c, dst);
@@ -348,32 +358,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (has_r2 && valid) r2p = p.R2 + row * p.ldr2 + obase;
         if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
       }
-      if ((has_r1 || has_r2) && tile + static_cast<int>(gridDim.x) < total_tiles) {
-        // pull the NEXT tile's residual row segments into L2 now; they are consumed one tile-time later
-        int u0, u1, u2;
-        tile_origin<CONV>(p, tw.m_tile, u0, u1, u2);
-        long long nrow;
-        if (map_row(u0, u1, u2, nrow)) {
-          const int ncol0 = tw.n_tile * OUT_COLS + c_begin_next * 16;
+      if (has_r1 || has_r2) {
+        // pull the residual row segments of the tile after next into L2 now (two tile-times of lead: these rows
+        // come from HBM); the first iteration also covers the next tile
+        auto prefetch_tile = [&](const TileWalk& w, int cb) {
+          int u0, u1, u2;
+          tile_origin<CONV>(p, w.m_tile, u0, u1, u2);
+          long long nrow;
+          if (map_row(u0, u1, u2, nrow)) {
+            const int ncol0 = w.n_tile * OUT_COLS + cb * 16;
 #pragma unroll
-          for (int off = 0; off < CH_HALF * 16; off += 64) {
-            if (has_r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + nrow * p.ldr1 + ncol0 + off));
-            if (has_r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R2 + nrow * p.ldr2 + ncol0 + off));
+            for (int off = 0; off < CH_HALF * 16; off += 64) {
+              if (has_r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R1 + nrow * p.ldr1 + ncol0 + off));
+              if (has_r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R2 + nrow * p.ldr2 + ncol0 + off));
+            }
           }
+        };
+        const int step = static_cast<int>(gridDim.x);
+        if (iter == 0 && tile + step < total_tiles) prefetch_tile(tw, c_begin_next);
+        if (tile + 2 * step < total_tiles) {
+          TileWalk tw2 = tw;
+          tw2.next();
+          prefetch_tile(tw2, c_begin);
         }
       }
 
       // residuals travel one load group ahead: group g+1's rows are requested before group g is processed, so they
       // have landed by the time the proxy fence (a full CTA memory barrier) of group g is reached
-      uint4 na[LG][2], nb[LG][2];
+      uint4 na[LG][2];
 #pragma unroll
-      for (int hh = 0; hh < LG; ++hh) na[hh][0] = na[hh][1] = nb[hh][0] = nb[hh][1] = make_uint4(0, 0, 0, 0);
+      for (int hh = 0; hh < LG; ++hh) na[hh][0] = na[hh][1] = make_uint4(0, 0, 0, 0);
       auto load_res = [&](int g) {
 #pragma unroll
         for (int hh = 0; hh < LG; ++hh) {
           const int c = (c_begin + g * LG + hh) * 16;
           if (r1p) { na[hh][0] = __ldg(reinterpret_cast<const uint4*>(r1p + c)); na[hh][1] = __ldg(reinterpret_cast<const uint4*>(r1p + c) + 1); }
-          if (r2p) { nb[hh][0] = __ldg(reinterpret_cast<const uint4*>(r2p + c)); nb[hh][1] = __ldg(reinterpret_cast<const uint4*>(r2p + c) + 1); }
         }
       };
       if (my_n > 0) load_res(0);
@@ -383,9 +402,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tmem_ld_wait();
           V3D_ETRACE();  // group: TMEM data landed
           if ((g + 1) * LG < my_n) issue_group(g + 1, vb[(g + 1) & 1]);
+          // the bias lines of the NEXT group (or of the next tile's first group) are pulled into L1 now: the residual
+          // stream of a tile is larger than L1, so a line fetched any earlier would be gone again
+          if (EPI != EPI_TRANS) {
+            const bool more = (g + 1) * LG < my_n;
+            const int ncol = more ? nbase + (c_begin + (g + 1) * LG) * 16 : tw.n_tile * BN + c_begin_next * 16;
+            if (has_bias && lane == 0) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + ncol));
+              if (GEGLU) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + ncol + BN / 2));
+            }
+            if (fb && more) asm volatile("prefetch.global.L1 [%0];" ::"l"(fb + (c_begin + (g + 1) * LG) * 16));
+          }
           uint4 ca[LG][2], cb[LG][2];
 #pragma unroll
-          for (int hh = 0; hh < LG; ++hh) { ca[hh][0] = na[hh][0]; ca[hh][1] = na[hh][1]; cb[hh][0] = nb[hh][0]; cb[hh][1] = nb[hh][1]; }
+          for (int hh = 0; hh < LG; ++hh) {
+            ca[hh][0] = na[hh][0];
+            ca[hh][1] = na[hh][1];
+            cb[hh][0] = cb[hh][1] = make_uint4(0, 0, 0, 0);
+            // the second residual (blend epilogue only) is fetched for the current group: its rows were pulled
+            // into L2 two tiles ago, and holding a second prefetched set would spill
+            if (r2p) {
+              const int c = (c_begin + g * LG + hh) * 16;
+              cb[hh][0] = __ldg(reinterpret_cast<const uint4*>(r2p + c));
+              cb[hh][1] = __ldg(reinterpret_cast<const uint4*>(r2p + c) + 1);
+            }
+          }
           if ((g + 1) * LG < my_n) load_res(g + 1);
 #pragma unroll
           for (int hh = 0; hh < LG; ++hh) {
@@ -394,72 +435,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t* v = &vb[g & 1][GEGLU ? 0 : hh * 16];
             const uint32_t* gv = &vb[g & 1][GEGLU ? 16 : 0];
             const uint4 ra0 = ca[hh][0], ra1 = ca[hh][1], rb0 = cb[hh][0], rb1 = cb[hh][1];
-            float f[16];
+            // all epilogue arithmetic runs on packed f32x2 pairs (FADD2 / FMUL2 / FFMA2: half the issue slots)
+            uint64_t f2[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) f2[j] = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
             // bias vectors are shared by every row: after the first warp touched them they are L1 hits
             if (EPI == EPI_TRANS) {
+              const uint64_t rb2 = pack2(row_bias, row_bias);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += row_bias;
+              for (int j = 0; j < 8; ++j) f2[j] = add2(f2[j], rb2);
             } else if (has_bias) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
-                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                f2[2 * j] = add2(f2[2 * j], pack2(b4.x, b4.y));
+                f2[2 * j + 1] = add2(f2[2 * j + 1], pack2(b4.z, b4.w));
               }
             }
             if (fb) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(fb + c) + j);
-                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                f2[2 * j] = add2(f2[2 * j], pack2(b4.x, b4.y));
+                f2[2 * j + 1] = add2(f2[2 * j + 1], pack2(b4.z, b4.w));
               }
             }
             if (GEGLU) {
-              float gt[16];
+              uint64_t g2[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(gv[j]);
+              for (int j = 0; j < 8; ++j) g2[j] = pack2(__uint_as_float(gv[2 * j]), __uint_as_float(gv[2 * j + 1]));
               if (has_bias) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + BN / 2 + c) + j);
-                  gt[4 * j] += b4.x; gt[4 * j + 1] += b4.y; gt[4 * j + 2] += b4.z; gt[4 * j + 3] += b4.w;
+                  g2[2 * j] = add2(g2[2 * j], pack2(b4.x, b4.y));
+                  g2[2 * j + 1] = add2(g2[2 * j + 1], pack2(b4.z, b4.w));
                 }
               }
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] *= gelu_erf_fast(gt[j]);
+              for (int j = 0; j < 8; ++j) f2[j] = mul2(f2[j], gelu_erf_fast2(g2[j]));
             } else if (EPI == EPI_F32 && do_silu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+              for (int j = 0; j < 8; ++j) {
+                float a, b;
+                unpack2(f2[j], a, b);
+                f2[j] = pack2(silu_f(a), silu_f(b));
+              }
             }
             if (r1p || r2p) {
-              float t[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) t[j] = 0.f;
+              const uint64_t s0v = pack2(s0, s0), s1v = pack2(s1, s1), s2v = pack2(s2, s2);
               if (r1p) {
                 const uint32_t u[8] = {ra0.x, ra0.y, ra0.z, ra0.w, ra1.x, ra1.y, ra1.z, ra1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float2 x2 = unpack_bf16x2(u[j]);
-                  t[2 * j] = s1 * x2.x;
-                  t[2 * j + 1] = s1 * x2.y;
+                  f2[j] = fma2(f2[j], s0v, mul2(pack2(x2.x, x2.y), s1v));
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f2[j] = mul2(f2[j], s0v);
               }
               if (r2p) {
                 const uint32_t u[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float2 x2 = unpack_bf16x2(u[j]);
-                  t[2 * j] = fmaf(s2, x2.x, t[2 * j]);
-                  t[2 * j + 1] = fmaf(s2, x2.y, t[2 * j + 1]);
+                  f2[j] = fma2(pack2(x2.x, x2.y), s2v, f2[j]);
                 }
               }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s0, t[j]);
             } else if (s0 != 1.0f) {
+              const uint64_t s0v = pack2(s0, s0);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] *= s0;
+              for (int j = 0; j < 8; ++j) f2[j] = mul2(f2[j], s0v);
             }
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) unpack2(f2[j], f[2 * j], f[2 * j + 1]);
             if (EPI == EPI_TRANS) {
               // D[col][row]: lanes hold consecutive rows -> each store instruction is one contiguous 128-byte line
               if (valid) {
@@ -478,28 +529,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
               }
-            } else if (!(p.dbg & 1)) {
+            } else if (!V3D_DBG(1)) {
               // bf16 rows leave through TMA.  The chunk goes into this row's slot of the group's current buffer
               // (64-byte rows, 64B-swizzled: conflict-free 16-byte stores); when the sub-tile is complete the
               // group meets on its named barrier and one thread issues the 128-row store, which the hardware
               // clips at the tensor edge (row tails, image tails).
               const uint32_t buf = stg + static_cast<uint32_t>((nstore & 1) * SUB_BYTES) + row_off;
               const int part = k % CPS;
-              if (!(p.dbg & 32)) {
+              if (!V3D_DBG(32)) {
                 sts128(buf + (((part * 2) ^ swz) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                 sts128(buf + (((part * 2 + 1) ^ swz) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
                        pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
               }
               if (part == CPS - 1) {
-                if (!(p.dbg & 16)) fence_proxy_async_smem();
+                if (!V3D_DBG(16)) fence_proxy_async_smem();
                 V3D_ETRACE();  // sub-tile rows written + fenced
                 // the previous store (other buffer) must have drained before anyone refills it after the barrier
-                if (store_leader && !(p.dbg & 8)) bulk_wait_read<0>();
+                if (store_leader && !V3D_DBG(8)) bulk_wait_read<0>();
                 V3D_ETRACE();  // previous store drained
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
                 V3D_ETRACE();  // group met
-                if (store_leader && !(p.dbg & 2)) {
+                if (store_leader && !V3D_DBG(2)) {
                   const uint32_t src = stg + static_cast<uint32_t>((nstore & 1) * SUB_BYTES);
                   const int col0 = obase + c - (CPS - 1) * 16;
                   if (CONV) tma_store_4d(&mapD, src, col0, t0, t1, t2);
@@ -608,8 +659,17 @@ using namespace v3d;
 /* diagnostics: device buffer of >= 3072 int64 that CTA 0 of every subsequent GEMM launch fills with clock64()
  * timelines (producer k-blocks | MMA issuer | epilogue warp 2); NULL disables. Not part of the product path. */
 extern "C" int v3d_debug_set_trace(void* buf) {
+#ifdef V3D_GEMM_DIAG
   g_trace = static_cast<long long*>(buf);
   return V3D_OK;
+#else
+  if (buf != nullptr) {
+    set_error("v3d_debug_set_trace: library built without V3D_GEMM_DIAG");
+    return V3D_ERR_UNSUPPORTED;
+  }
+  g_trace = nullptr;
+  return V3D_OK;
+#endif
 }
 
 extern "C" int v3d_gemm_pick_block_n(int32_t N, int32_t act) { return pick_block_n(N, act); }
