@@ -33,6 +33,7 @@ struct GemmEpi {
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
   int rows_per_frame, act, out_fp32;
   int b_batched;
+  int fb_uniform;  // every 32-row warp slice of a tile lies in one frame: per-frame bias folds into the bias registers
   long long* trace;  // diagnostics only: CTA 0 writes role timelines (clock64) here when non-null
   // diagnostics only (V3D_GEMM_DEBUG): 1 = skip the store path, 2 = skip TMA store issue, 4 = skip TMEM loads,
   // 8 = skip the drain wait, 16 = skip the proxy fence, 32 = skip the smem writes.  Results are wrong with any bit set.
@@ -294,6 +295,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int LG = GEGLU ? 1 : CPS;          // 16-column output chunks per load group
     constexpr int LREGS = GEGLU ? 32 : 16 * LG;  // registers per buffer
     constexpr int NG_HALF = CH_HALF / LG;
+    constexpr int NBR = (CH_HALF * 16 + 31) / 32;  // bias registers per lane
+    // tile row -> (valid, global row). bw/bh are powers of two (checked on the host).
+    auto map_row_of = [&](int tr, int o0, int o1, int o2, long long& grow) -> bool {
+      if (CONV) {
+        const int w = tr & (p.bw - 1);
+        const int h = (tr >> p.bw_shift) & (p.bh - 1);
+        const int img = o2 + (tr >> (p.bw_shift + p.bh_shift));
+        grow = (static_cast<long long>(img) * p.ch + (o1 + h)) * p.cw + (o0 + w);
+        return img < p.cn;
+      } else {
+        const int m = o1 + tr;
+        grow = static_cast<long long>(o0) * p.rows_per_batch + m;
+        return m < p.rows_per_batch;
+      }
+    };
     TileWalk tw(p);
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -328,20 +344,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       };
       if (my_n > 0) issue_group(0, vb[0]);
+      // bias for this warp's columns, one coalesced load per tile, spread over the lanes (column i*32+lane of the
+      // warp's slice) and handed out by shuffles in the chunk loop: no memory latency inside the loop.  A per-frame
+      // bias that is uniform over the warp's rows is folded in here.
+      float breg[NBR], greg[GEGLU ? NBR : 1];
+      {
+        const float* fbw = nullptr;
+        if (has_fb && p.fb_uniform) {
+          long long rw;
+          if (map_row_of(q * 32, t0, t1, t2, rw))
+            fbw = p.fbias + static_cast<long long>(static_cast<int>(rw) / p.rows_per_frame) * p.ldfb + n_tile * BN;
+        }
+#pragma unroll
+        for (int i = 0; i < NBR; ++i) {
+          const int col = c_begin * 16 + i * 32 + lane;
+          const bool ok = i * 32 + lane < my_n * 16;
+          float bvv = 0.f;
+          if (EPI != EPI_TRANS && has_bias && ok) bvv = __ldg(p.bias + n_tile * BN + col);
+          if (fbw && ok) bvv += __ldg(fbw + col);
+          breg[i] = bvv;
+          if (GEGLU) greg[i] = (has_bias && ok) ? __ldg(p.bias + n_tile * BN + BN / 2 + col) : 0.f;
+        }
+      }
 
       // tile row -> (valid, global row). bw/bh are powers of two (checked on the host).
       auto map_row = [&](int o0, int o1, int o2, long long& grow) -> bool {
-        if (CONV) {
-          const int w = r & (p.bw - 1);
-          const int h = (r >> p.bw_shift) & (p.bh - 1);
-          const int img = o2 + (r >> (p.bw_shift + p.bh_shift));
-          grow = (static_cast<long long>(img) * p.ch + (o1 + h)) * p.cw + (o0 + w);
-          return img < p.cn;
-        } else {
-          const int m = o1 + r;
-          grow = static_cast<long long>(o0) * p.rows_per_batch + m;
-          return m < p.rows_per_batch;
-        }
+        return map_row_of(r, o0, o1, o2, grow);
       };
       const int obase = n_tile * OUT_COLS;  // first output column of this tile
       const int nbase = n_tile * BN;        // first column in the (packed) N space
@@ -351,9 +379,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bf16* r1p = nullptr;
       const bf16* r2p = nullptr;
       float row_bias = 0.f;
-      if (!STAGED || has_fb || has_r1 || has_r2) {  // plain bf16 tiles never need per-row addresses
+      if (!STAGED || (has_fb && !p.fb_uniform) || has_r1 || has_r2) {  // plain bf16 tiles never need per-row addresses
         valid = map_row(t0, t1, t2, row);
-        if (has_fb && valid) fb = p.fbias + static_cast<long long>(static_cast<int>(row) / p.rows_per_frame) * p.ldfb + nbase;
+        if (has_fb && !p.fb_uniform && valid) fb = p.fbias + static_cast<long long>(static_cast<int>(row) / p.rows_per_frame) * p.ldfb + nbase;
         if (has_r1 && valid) r1p = p.R1 + row * p.ldr1 + obase;
         if (has_r2 && valid) r2p = p.R2 + row * p.ldr2 + obase;
         if (EPI == EPI_TRANS && has_bias && valid) row_bias = __ldg(p.bias + row);
@@ -402,17 +430,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tmem_ld_wait();
           V3D_ETRACE();  // group: TMEM data landed
           if ((g + 1) * LG < my_n) issue_group(g + 1, vb[(g + 1) & 1]);
-          // the bias lines of the NEXT group (or of the next tile's first group) are pulled into L1 now: the residual
-          // stream of a tile is larger than L1, so a line fetched any earlier would be gone again
-          if (EPI != EPI_TRANS) {
-            const bool more = (g + 1) * LG < my_n;
-            const int ncol = more ? nbase + (c_begin + (g + 1) * LG) * 16 : tw.n_tile * BN + c_begin_next * 16;
-            if (has_bias && lane == 0) {
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + ncol));
-              if (GEGLU) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + ncol + BN / 2));
-            }
-            if (fb && more) asm volatile("prefetch.global.L1 [%0];" ::"l"(fb + (c_begin + (g + 1) * LG) * 16));
-          }
           uint4 ca[LG][2], cb[LG][2];
 #pragma unroll
           for (int hh = 0; hh < LG; ++hh) {
@@ -444,12 +461,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const uint64_t rb2 = pack2(row_bias, row_bias);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f2[j] = add2(f2[j], rb2);
-            } else if (has_bias) {
+            } else if (has_bias || (has_fb && p.fb_uniform)) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c) + j);
-                f2[2 * j] = add2(f2[2 * j], pack2(b4.x, b4.y));
-                f2[2 * j + 1] = add2(f2[2 * j + 1], pack2(b4.z, b4.w));
+              for (int j = 0; j < 8; ++j) {
+                const float b0 = __shfl_sync(0xffffffffu, breg[(k * 16 + 2 * j) >> 5], (k * 16 + 2 * j) & 31);
+                const float b1 = __shfl_sync(0xffffffffu, breg[(k * 16 + 2 * j + 1) >> 5], (k * 16 + 2 * j + 1) & 31);
+                f2[j] = add2(f2[j], pack2(b0, b1));
               }
             }
             if (fb) {
@@ -466,10 +483,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int j = 0; j < 8; ++j) g2[j] = pack2(__uint_as_float(gv[2 * j]), __uint_as_float(gv[2 * j + 1]));
               if (has_bias) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + BN / 2 + c) + j);
-                  g2[2 * j] = add2(g2[2 * j], pack2(b4.x, b4.y));
-                  g2[2 * j + 1] = add2(g2[2 * j + 1], pack2(b4.z, b4.w));
+                for (int j = 0; j < 8; ++j) {
+                  const float b0 = __shfl_sync(0xffffffffu, greg[(k * 16 + 2 * j) >> 5], (k * 16 + 2 * j) & 31);
+                  const float b1 = __shfl_sync(0xffffffffu, greg[(k * 16 + 2 * j + 1) >> 5], (k * 16 + 2 * j + 1) & 31);
+                  g2[j] = add2(g2[j], pack2(b0, b1));
                 }
               }
 #pragma unroll
@@ -778,6 +795,16 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     }
     e.dbg = dbg;
     e.trace = g_trace;
+  }
+  if (a->fbias != nullptr) {
+    if (conv) {
+      const int bw_ = a->conv_w < BM ? a->conv_w : BM;
+      int bh_ = BM / bw_;
+      if (bh_ > a->conv_h) bh_ = a->conv_h;
+      e.fb_uniform = (bw_ * bh_) % 32 == 0 && e.rows_per_frame % (a->conv_w * a->conv_h) == 0;
+    } else {
+      e.fb_uniform = e.rows_per_frame % 32 == 0 && (a->batch <= 1 || a->rows_per_batch % 32 == 0);
+    }
   }
   e.transposed = a->out_transposed;
   e.valid_cols = a->valid_cols > 0 ? a->valid_cols : a->N;
