@@ -190,7 +190,8 @@ if __name__ == "__main__":
         for _ in range(3):
             ops.gemm(a, w, o, K=K, N=N, rows_per_batch=M)
         buf = torch.zeros(3072, device=DEV, dtype=torch.int64)
-        _lib.load().v3d_debug_set_trace(buf.data_ptr())
+        if _lib.load().v3d_debug_set_trace(buf.data_ptr()) != 0:
+            sys.exit("trace needs a diagnostics build: V3D_GEMM_DIAG=1 python -m v3d_b200.build")
         ops.gemm(a, w, o, K=K, N=N, rows_per_batch=M)
         torch.cuda.synchronize()
         _lib.load().v3d_debug_set_trace(None)
