@@ -114,19 +114,26 @@ def _cpu_threads() -> int:
 
 
 class CpuReference:
-    """Oracle port (oracle/, kind "port") of the reference path. One `sample()` = one CFG-batched UNet forward
-    (B = 2T) at T frames on a latent_u x latent_u latent + one first-stage decode of T frames on a
-    latent_d x latent_d latent, fp32, all host threads; extrapolated to the full workload by pixel count
-    (the attention N^2 term is under-counted by this scaling, which favours the CPU number)."""
+    """Oracle port (oracle/, kind "port") of the reference path, fp32, on the host cores.
 
-    def __init__(self, T: int, S: int, latent: int, latent_u: int = 16, latent_d: int = 8):
+    One `sample()` = one CFG-batched UNet forward (B = 2T, T frames) at TWO latent sizes + one first-stage decode of
+    T frames at TWO latent sizes.  The time at the full latent is the affine model  t(L) = a + b * L^2  through the
+    two measurements (a = per-forward fixed cost: ~2.4k small ops and 6 GB of fp32 weights; b = per-pixel cost), so the
+    fixed cost is not multiplied by the pixel ratio; the attention N^2 term is under-counted by this model, which
+    favours the CPU number.  The thread count is calibrated once (more threads than the box can really run make the
+    many small ops slower, not faster): `cores` in the JSON is the count actually used."""
+
+    # (UNet latents, decoder latents, cost of one sample in units of the calibration forward); V3D_512 itself is 64
+    LADDER = (((16, 32), (8, 16), 20.0), ((8, 16), (4, 8), 5.5))
+    BUDGET_S = 240.0     # all samples of a run (warm-up + timed) should fit in about this much CPU time
+
+    def __init__(self, T: int, S: int, latent: int, n_samples: int = 1):
         import torch
         from oracle import ref_decoder, ref_unet  # the one place bench.py executes oracle/: the timed baseline
 
         self.torch, self.ref_unet, self.ref_decoder = torch, ref_unet, ref_decoder
-        self.T, self.S, self.latent, self.lu, self.ld = T, S, latent, min(latent_u, latent), min(latent_d, latent)
-        self.threads = _cpu_threads()
-        torch.set_num_threads(self.threads)
+        self.T, self.S, self.latent = T, S, latent
+        self.n_samples = max(1, n_samples)
         self.spec_u = ref_unet.UNetSpec()
         self.spec_d = ref_decoder.DecoderSpec()
         g = torch.Generator().manual_seed(0)
@@ -145,39 +152,92 @@ class CpuReference:
         self.sd_u = {k: rnd(s, k) for k, s in ref_unet.unet_param_shapes(self.spec_u).items()}
         self.sd_d = {k: rnd(s, k) for k, s in ref_decoder.decoder_param_shapes(self.spec_d).items()}
         B = 2 * T
-        self.xin = torch.randn(B, 8, self.lu, self.lu, generator=g)
+        self.xin = {8: torch.randn(B, 8, 8, 8, generator=g)}
         self.ts = torch.full((B,), 0.3)
         self.ctx = torch.randn(B, 1, 1024, generator=g)
         self.y = torch.randn(B, 768, generator=g)
         self.ind = torch.zeros(2, T)
-        self.z = torch.randn(T, 4, self.ld, self.ld, generator=g)
+        self.threads, self.thread_trials = self._calibrate_threads()
+        torch.set_num_threads(self.threads)
+        # the largest sample sizes whose predicted cost fits the run's CPU-time budget
+        t_cal = self.thread_trials[self.threads]
+        su, sdz = self.LADDER[-1][:2]
+        for lu, ldz, cost in self.LADDER:
+            if cost * t_cal * self.n_samples <= self.BUDGET_S:
+                su, sdz = lu, ldz
+                break
+        self.su = tuple(min(x, latent) for x in su)
+        self.sdz = tuple(min(x, latent) for x in sdz)
+        for L in self.su:
+            self.xin.setdefault(L, torch.randn(B, 8, L, L, generator=g))
+        self.z = {L: torch.randn(T, 4, L, L, generator=g) for L in set(self.sdz)}
+
+    def _unet(self, L: int) -> float:
+        t0 = time.perf_counter()
+        self.ref_unet.unet_forward(self.sd_u, self.spec_u, self.xin[L], self.ts, self.ctx, self.y, self.T, self.ind)
+        return time.perf_counter() - t0
+
+    def _dec(self, L: int) -> float:
+        t0 = time.perf_counter()
+        self.ref_decoder.decoder_forward(self.sd_d, self.spec_d, self.z[L], self.T)
+        return time.perf_counter() - t0
+
+    def _calibrate_threads(self):
+        """Smallest UNet forward (latent 8) at 8, 16, 32, ... threads up to the affinity mask; stop once a step is
+        clearly slower than the best so far.  Returns (best, {threads: seconds})."""
+        torch = self.torch
+        ncpu = _cpu_threads()
+        cands = sorted({min(c, ncpu) for c in (8, 16, 32, 64, 128, 256)} | {ncpu})
+        trials, best_n, best_t = {}, cands[0], None
+        with torch.no_grad():
+            torch.set_num_threads(cands[0])
+            self._unet(8)  # first call pays allocator / oneDNN primitive setup
+            for n in cands:
+                torch.set_num_threads(n)
+                t = self._unet(8)
+                trials[n] = round(t, 3)
+                if best_t is None or t < best_t:
+                    best_n, best_t = n, t
+                elif t > 1.5 * best_t:
+                    break
+        return best_n, trials
 
     def sample(self):
-        torch = self.torch
-        with torch.no_grad():
-            t0 = time.perf_counter()
-            self.ref_unet.unet_forward(self.sd_u, self.spec_u, self.xin, self.ts, self.ctx, self.y, self.T, self.ind)
-            t1 = time.perf_counter()
-            self.ref_decoder.decoder_forward(self.sd_d, self.spec_d, self.z, self.T)
-            t2 = time.perf_counter()
-        return t1 - t0, t2 - t1
+        """-> (seconds of one UNet forward extrapolated to the full latent, seconds of the full decode), plus the
+        raw measurements in self.last"""
+        with self.torch.no_grad():
+            tu = [self._unet(L) for L in self.su]
+            td = [self._dec(L) for L in self.sdz]
+        self.last = {"unet_s": dict(zip(self.su, (round(t, 3) for t in tu))),
+                     "decode_s": dict(zip(self.sdz, (round(t, 3) for t in td)))}
+        return self._affine(self.su, tu), self._affine(self.sdz, td)
 
-    def frames_per_sec(self, t_unet: float, t_dec: float) -> float:
-        ku = (self.latent / self.lu) ** 2
-        kd = (self.latent / self.ld) ** 2
-        return self.T / (self.S * t_unet * ku + t_dec * kd)
+    def _affine(self, sizes, times) -> float:
+        (l0, l1), (t0, t1) = sizes, times
+        full = float(self.latent) ** 2
+        if l1 > l0:
+            b = (t1 - t0) / (l1 * l1 - l0 * l0)
+            a = t0 - b * l0 * l0
+            if b > 0 and a >= 0:
+                return a + b * full
+        return t1 * full / (l1 * l1)  # degenerate fit (noise, or sizes clipped to the latent): plain pixel scaling
+
+    def frames_per_sec(self, t_unet_full: float, t_dec_full: float) -> float:
+        return self.T / (self.S * t_unet_full + t_dec_full)
 
     def describe(self) -> str:
-        return (f"oracle port fp32, {self.threads} threads: 1 CFG-batched UNet forward (B={2 * self.T}, T={self.T}, "
-                f"latent {self.lu}x{self.lu}) + 1 decode (T={self.T}, latent {self.ld}x{self.ld}); extrapolated to "
-                f"latent {self.latent}x{self.latent} by pixel count and to {self.S} EDM steps (steps are cost-identical)")
+        return (f"oracle port fp32, {self.threads} threads (calibrated over {sorted(self.thread_trials)}): per sample one "
+                f"CFG-batched UNet forward (B={2 * self.T}, T={self.T}) at latents {self.su[0]}^2 and {self.su[1]}^2 "
+                f"and one decode (T={self.T}) at latents {self.sdz[0]}^2 and {self.sdz[1]}^2; each extrapolated to "
+                f"latent {self.latent}^2 by the affine model t = a + b*pixels through its two sizes, UNet x {self.S} "
+                f"EDM steps (steps are cost-identical)")
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref = CpuReference(args.frames, args.edm_steps, args.latent)
+    ref = CpuReference(args.frames, args.edm_steps, args.latent, n_samples=args.steps + args.warmup)
     for _ in range(args.warmup):
         ref.sample()
     tu = td = 0.0
@@ -195,7 +255,8 @@ def run_reference(args) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "cpu"),
         "cpu_baseline": {"value": v, "unit": "view-frames/s", "cores": ref.threads, "kind": "port",
-                         "sample": ref.describe(), "t_unet_sample_s": tu, "t_decode_sample_s": td},
+                         "sample": ref.describe(), "t_unet_forward_full_s": tu, "t_decode_full_s": td,
+                         "last_sample_raw_s": ref.last, "thread_calibration_s": ref.thread_trials},
         "e2e": {"value": v, "unit": "view-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -422,8 +483,9 @@ def run_native(args) -> None:
         ref = CpuReference(T, S, L)
         tu, td = ref.sample()
         line["cpu_baseline"] = {"value": ref.frames_per_sec(tu, td), "unit": "view-frames/s", "cores": ref.threads,
-                                "kind": "port", "sample": ref.describe(), "t_unet_sample_s": tu,
-                                "t_decode_sample_s": td}
+                                "kind": "port", "sample": ref.describe(), "t_unet_forward_full_s": tu,
+                                "t_decode_full_s": td, "last_sample_raw_s": ref.last,
+                                "thread_calibration_s": ref.thread_trials}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
