@@ -185,6 +185,10 @@ int v3d_cfg_combine(const void* den, const void* scale, void* out, int32_t B, in
 /* to_d + euler_step (sampling_utils.py:34-35; sampling.py:81-82,103-106); out may alias x. */
 int v3d_euler_step(const void* x, const void* den, const void* sigma_hat, const void* sigma_next, void* out,
                    int32_t nsamples, int64_t per_sample, void* stream);
+/* HeunEDMSampler.possible_correction_step (sampling.py:221-237): x + dt * (d + d_new) / 2 where sigma_next > 0,
+ * else the Euler proposal; x_euler = euler step of x, den2 = denoised(x_euler, sigma_next). out may alias x. */
+int v3d_heun_step(const void* x, const void* den, const void* x_euler, const void* den2, const void* sigma_hat,
+                  const void* sigma_next, void* out, int32_t nsamples, int64_t per_sample, void* stream);
 /* clamp((x+1)/2,0,1)*255 -> uint8 THWC from the decoder's NHWC output (scripts/pub/V3D_512.py:286-303). */
 int v3d_decode_to_u8(const void* x, int64_t ldx, int32_t src_fp32, void* y, int64_t npix, void* stream);
 /* same, from NCHW fp32 frames [T][3][HW] (decode_first_stage's return layout) to uint8 [T][HW][3]. */

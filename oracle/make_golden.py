@@ -102,6 +102,38 @@ def _edm_step_case(ns, net, sd, spec, tag: str, T: int, hw: int, num_steps: int,
     return ref
 
 
+def _sampler_variant_case(ns, net, sd, spec, tag: str, T: int, hw: int, num_steps: int, sampler_cls: str,
+                          guider: str, manifest: dict):
+    """the other samplers / guiders on the same denoiser (Heun; VanillaCFG; CentralPredictionGuider)."""
+    x, c, uc = synth.synth_inputs(T, hw)
+    gparams = {"linear": ("LinearPredictionGuider", {"max_scale": 3.5, "min_scale": 1.5, "num_frames": T}),
+               "central": ("CentralPredictionGuider", {"max_scale": 3.5, "min_scale": 1.5, "num_frames": T}),
+               "vanilla": ("VanillaCFG", {"scale": 2.5})}[guider]
+    sampler = getattr(ns.sampling, sampler_cls)(
+        num_steps=num_steps,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                               "params": {"sigma_max": 700.0}},
+        guider_config={"target": "sgm.modules.diffusionmodules.guiders." + gparams[0], "params": gparams[1]},
+        device="cpu")
+    den = ns.denoiser.Denoiser({"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"})
+    wrapped = ns.wrappers.OpenAIWrapper(net)
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    scale, nf = {"linear": (ref_sampling.guider_scale(1.5, 3.5, T), T),
+                 "central": (ref_sampling.central_guider_scale(1.5, 3.5, T), T),
+                 "vanilla": (ref_sampling.vanilla_scale(2.5), 1)}[guider]
+    fn = ref_sampling.heun_edm_sample if sampler_cls == "HeunEDMSampler" else ref_sampling.euler_edm_sample
+    with torch.no_grad():
+        ref = sampler(lambda i, s, cc: den(wrapped, i, s, cc, **extra), x.clone(), cond=c, uc=uc)
+        ora = fn(lambda i, s, cc: ref_sampling.denoiser(
+            lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd, spec, xx, tt, cond, **kw), i, s, cc, **extra),
+            x.clone(), c, uc, num_steps, scale, nf)
+    err = _pin(tag, ref, ora)
+    torch.save({"out": ref}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="edm_sample_variant", sampler=sampler_cls, guider=guider, T=T, latent_hw=hw,
+                         num_steps=num_steps, min_scale=1.5, max_scale=3.5, vanilla_scale=2.5, sigma_max=700.0,
+                         pin_err=err, out_std=ref.std().item())
+
+
 def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, manifest: dict, z=None):
     kw = dict(reference_shim.V3D_DECODER_KW)
     kw["ch"] = ch
@@ -138,9 +170,16 @@ def main(argv):
     def want(tag):
         return not only or tag in only
 
-    if want("unet_small") or want("edm_small"):
+    variants = {"edm_small_heun": ("HeunEDMSampler", "linear"), "edm_small_central": ("EulerEDMSampler", "central"),
+                "edm_small_vanilla": ("EulerEDMSampler", "vanilla")}
+    if want("unet_small") or want("edm_small") or any(want(v) for v in variants):
         net, sd, spec = _unet_case(ns, "unet_small", 64, T=4, hw=32, wseed=1, sigma=3.0, manifest=manifest)
-        _edm_step_case(ns, net, sd, spec, "edm_small", T=4, hw=32, num_steps=3, manifest=manifest)
+        if want("edm_small"):
+            _edm_step_case(ns, net, sd, spec, "edm_small", T=4, hw=32, num_steps=3, manifest=manifest)
+        for vtag, (scls, gd) in variants.items():
+            if want(vtag):
+                _sampler_variant_case(ns, net, sd, spec, vtag, T=4, hw=32, num_steps=3, sampler_cls=scls, guider=gd,
+                                      manifest=manifest)
     if want("unet_small_t18"):
         _unet_case(ns, "unet_small_t18", 64, T=18, hw=16, wseed=2, sigma=40.0, manifest=manifest)
     if want("unet_full") or want("edm_full_step"):
@@ -158,6 +197,10 @@ def main(argv):
         disc = ns.discretizer.EDMDiscretization(sigma_max=700.0)
         blob = {f"sigmas_{n}": disc(n) for n in (1, 10, 25, 50)}
         blob["guider_scale_18"] = ns.guiders.LinearPredictionGuider(max_scale=3.5, min_scale=1.0, num_frames=18).scale
+        blob["central_scale_18"] = ns.guiders.CentralPredictionGuider(max_scale=3.5, min_scale=1.0, num_frames=18).scale
+        blob["central_scale_25"] = ns.guiders.CentralPredictionGuider(max_scale=2.5, min_scale=1.0, num_frames=25).scale
+        assert torch.equal(blob["central_scale_18"], ref_sampling.central_guider_scale(1.0, 3.5, 18))
+        assert torch.equal(blob["central_scale_25"], ref_sampling.central_guider_scale(1.0, 2.5, 25))
         for n in (1, 10, 25, 50):
             assert torch.equal(blob[f"sigmas_{n}"], ref_sampling.edm_sigmas(n))
         assert torch.equal(blob["guider_scale_18"], ref_sampling.guider_scale(1.0, 3.5, 18))

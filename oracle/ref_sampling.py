@@ -2,7 +2,8 @@
 
 EDMDiscretization (discretizer.py:18-39), LinearPredictionGuider (guiders.py:60-101), Denoiser with
 VScalingWithEDMcNoise (denoiser.py:23-39, denoiser_scaling.py:51-59), EulerEDMSampler
-(sampling.py:44-55,96-133,214-218; sampling_utils.py:34-35).
+(sampling.py:44-55,96-133,214-218; sampling_utils.py:34-35); HeunEDMSampler (sampling.py:221-237), VanillaCFG
+(guiders.py:23-42), CentralPredictionGuider (guiders.py:104-146).
 """
 from __future__ import annotations
 
@@ -22,6 +23,18 @@ def edm_sigmas(n: int, sigma_min: float = 0.002, sigma_max: float = 700.0, rho: 
 
 def guider_scale(min_scale: float, max_scale: float, num_frames: int) -> torch.Tensor:
     return torch.linspace(min_scale, max_scale, num_frames).unsqueeze(0)  # guiders.py:71
+
+
+def central_guider_scale(min_scale: float, max_scale: float, num_frames: int) -> torch.Tensor:
+    """CentralPredictionGuider.__init__ (guiders.py:112-120): ramp to 2*max, second half mirrored."""
+    scale = torch.linspace(min_scale, 2 * max_scale, num_frames)
+    scale[num_frames // 2:] = 2 * max_scale - scale[num_frames // 2:]
+    return scale.unsqueeze(0)
+
+
+def vanilla_scale(scale: float) -> torch.Tensor:
+    """VanillaCFG (guiders.py:23-31) as a one-frame scale row for guider_combine(…, num_frames=1)."""
+    return torch.tensor([[float(scale)]])
 
 
 def guider_prepare_inputs(x, s, c: Dict, uc: Dict):
@@ -68,3 +81,30 @@ def euler_edm_sample(denoise_fn: Callable, x, cond: Dict, uc: Dict, num_steps: i
         if trace is not None:
             trace.append(x.clone())
     return x
+
+
+def heun_edm_sample(denoise_fn: Callable, x, cond: Dict, uc: Dict, num_steps: int, scale: torch.Tensor,
+                    num_frames: int, sigma_max: float = 700.0):
+    """HeunEDMSampler.__call__ with s_churn=0: the Euler proposal, then (unless every next sigma is 0) a second
+    denoiser evaluation at next_sigma and the step redone with the mean slope (sampling.py:96-133,221-237)."""
+    sigmas = edm_sigmas(num_steps, sigma_max=sigma_max)
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    bc = lambda v: v.reshape(-1, *([1] * (x.ndim - 1)))  # noqa: E731
+
+    def denoise(xx, sig):
+        return guider_combine(denoise_fn(*guider_prepare_inputs(xx, sig, cond, uc)), scale, num_frames)
+
+    for i in range(len(sigmas) - 1):
+        sigma_hat = s_in * sigmas[i]
+        next_sigma = s_in * sigmas[i + 1]
+        d = (x - denoise(x, sigma_hat)) / bc(sigma_hat)
+        dt = bc(next_sigma - sigma_hat)
+        x_euler = x + dt * d
+        if torch.sum(next_sigma) < 1e-14:
+            x = x_euler
+            continue
+        d_new = (x_euler - denoise(x_euler, next_sigma)) / bc(next_sigma)
+        x = torch.where(bc(next_sigma) > 0.0, x + (d + d_new) / 2.0 * dt, x_euler)
+    return x
+

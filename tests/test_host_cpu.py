@@ -136,6 +136,34 @@ def test_guider_and_discretizer_host_logic():
     assert bool((s[1:] < s[:-1]).all())
 
 
+def test_other_guiders_host_logic_bit_exact():
+    """CentralPredictionGuider / VanillaCFG scale rows equal the reference's (golden schedule.pt); [uc; c] order."""
+    from pathlib import Path
+
+    from v3d_b200 import sampling
+
+    gold = torch.load(Path(__file__).resolve().parent / "golden" / "schedule.pt")
+    g = sampling.CentralPredictionGuider(max_scale=3.5, min_scale=1.0, num_frames=18)
+    assert torch.equal(g.scale, gold["central_scale_18"])
+    assert torch.equal(sampling.CentralPredictionGuider(max_scale=2.5, num_frames=25).scale, gold["central_scale_25"])
+    v = sampling.VanillaCFG(scale=2.5)
+    assert v.num_frames == 1 and v.scale_value == 2.5 and tuple(v.scale.shape) == (1, 1)
+    v.scale = 4.0  # callers re-assign a python float (guiders.py:24-25)
+    assert v.scale_value == 4.0
+    c = {"vector": torch.ones(2, 3), "crossattn": torch.ones(2, 1, 2), "concat": torch.ones(2, 2, 2, 2)}
+    uc = {k: torch.zeros_like(t) for k, t in c.items()}
+    for guider in (g, v):
+        x2, s2, c2 = guider.prepare_inputs(torch.randn(2, 2, 2, 2), torch.full((2,), 7.0), c, uc)
+        assert x2.shape[0] == 4 and s2.shape[0] == 4
+        for k in c:
+            assert c2[k][:2].abs().sum() == 0 and torch.equal(c2[k][2:], c[k])
+    # the second-order sampler refuses CPU tensors like the first-order one (no CPU fallback)
+    smp = sampling.HeunEDMSampler(num_steps=2, discretization_config={
+        "target": "v3d_b200.sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": {"sigma_max": 700.0}})
+    with pytest.raises(RuntimeError):
+        smp(lambda *a: None, torch.randn(2, 4, 8, 8), cond={}, uc={})
+
+
 def test_drop_in_targets_resolve():
     from v3d_b200.sampling import get_obj_from_str
 
@@ -143,6 +171,9 @@ def test_drop_in_targets_resolve():
                        "sgm.modules.diffusionmodules.denoiser.Denoiser",
                        "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise",
                        "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+                       "sgm.modules.diffusionmodules.sampling.HeunEDMSampler",
+                       "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                       "sgm.modules.diffusionmodules.guiders.CentralPredictionGuider",
                        "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
                        "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
                        "sgm.modules.diffusionmodules.wrappers.OpenAIWrapper",

@@ -55,6 +55,27 @@ def test_oracle_edm_sampler_vs_reference_golden():
     assert _close(out, gold["out"])
 
 
+@pytest.mark.parametrize("tag", ["edm_small_heun", "edm_small_central", "edm_small_vanilla"])
+def test_oracle_sampler_variants_vs_reference_golden(tag):
+    """HeunEDMSampler, CentralPredictionGuider and VanillaCFG around the same denoiser."""
+    m, mu = MANIFEST[tag], MANIFEST["unet_small"]
+    gold = torch.load(GOLD / f"{tag}.pt")
+    spec = ref_unet.UNetSpec(model_channels=mu["model_channels"])
+    sd = synth.synth_state_dict(ref_unet.unet_param_shapes(spec), seed=mu["weight_seed"])
+    T = m["T"]
+    x, c, uc = synth.synth_inputs(T, m["latent_hw"])
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    scale, nf = {"linear": (ref_sampling.guider_scale(m["min_scale"], m["max_scale"], T), T),
+                 "central": (ref_sampling.central_guider_scale(m["min_scale"], m["max_scale"], T), T),
+                 "vanilla": (ref_sampling.vanilla_scale(m["vanilla_scale"]), 1)}[m["guider"]]
+    fn = ref_sampling.heun_edm_sample if m["sampler"] == "HeunEDMSampler" else ref_sampling.euler_edm_sample
+    with torch.no_grad():
+        out = fn(lambda i, s, cc: ref_sampling.denoiser(
+            lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd, spec, xx, tt, cond, **kw), i, s, cc, **extra),
+            x.clone(), c, uc, m["num_steps"], scale, nf)
+    assert _close(out, gold["out"])
+
+
 @pytest.mark.parametrize("tag", ["decoder_small", "decoder_small_2videos", "decoder_full"])
 def test_oracle_decoder_vs_reference_golden(tag):
     m = MANIFEST[tag]
@@ -73,6 +94,8 @@ def test_oracle_schedule_bit_exact():
         assert torch.equal(s, gold[f"sigmas_{n}"])
         assert s.shape[0] == n + 1 and s[-1] == 0 and bool((s[:-1][1:] < s[:-1][:-1]).all() if n > 1 else True)
     assert torch.equal(ref_sampling.guider_scale(1.0, 3.5, 18), gold["guider_scale_18"])
+    assert torch.equal(ref_sampling.central_guider_scale(1.0, 3.5, 18), gold["central_scale_18"])
+    assert torch.equal(ref_sampling.central_guider_scale(1.0, 2.5, 25), gold["central_scale_25"])
 
 
 def test_oracle_cfg_order_and_chunking():

@@ -72,6 +72,7 @@ SIGNATURES = {
     "v3d_edm_denoise_combine": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "v3d_cfg_combine": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "v3d_euler_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "v3d_heun_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "v3d_decode_to_u8": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "v3d_frames_nchw_to_u8": (C.c_int, [_vp, _vp, _i32, _i64, _vp]),
 }

@@ -68,6 +68,28 @@ __global__ void euler_step_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// Heun correction: d = (x - den)/sigma_hat, d2 = (x_euler - den2)/sigma_next,
+// out = sigma_next > 0 ? x + (sigma_next - sigma_hat) * (d + d2) / 2 : x_euler
+__global__ void heun_step_kernel(const float* __restrict__ x, const float* __restrict__ den,
+                                 const float* __restrict__ x_euler, const float* __restrict__ den2,
+                                 const float* __restrict__ sigma_hat, const float* __restrict__ sigma_next,
+                                 float* __restrict__ out, int nsamples, long long per_sample) {
+  const long long total = nsamples * per_sample;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / per_sample;
+    const float sh = sigma_hat[n], sn = sigma_next[n];
+    const float xe = x_euler[i];
+    float r = xe;
+    if (sn > 0.0f) {
+      const float d = (x[i] - den[i]) / sh;
+      const float d2 = (xe - den2[i]) / sn;
+      r = x[i] + ((d + d2) / 2.0f) * (sn - sh);
+    }
+    out[i] = r;
+  }
+}
+
 // frames[p][c] = uint8(clamp((x[p][c] + 1) / 2, 0, 1) * 255)  (truncating cast, like numpy astype)
 template <typename T>
 __global__ void decode_to_u8_kernel(const T* __restrict__ x, long long ldx, uint8_t* __restrict__ y, long long npix) {
@@ -156,6 +178,23 @@ int v3d_euler_step(const void* x, const void* den, const void* sigma_hat, const 
       static_cast<const float*>(x), static_cast<const float*>(den), static_cast<const float*>(sigma_hat),
       static_cast<const float*>(sigma_next), static_cast<float*>(out), nsamples, per_sample);
   V3D_CHECK_LAUNCH("euler_step_kernel");
+  return V3D_OK;
+}
+
+/* HeunEDMSampler.possible_correction_step (sampling.py:221-237): second-order correction from the Euler proposal
+ * x_euler and its denoised estimate den2 at sigma_next; samples with sigma_next == 0 keep the Euler proposal.
+ * out may alias x or x_euler. */
+int v3d_heun_step(const void* x, const void* den, const void* x_euler, const void* den2, const void* sigma_hat,
+                  const void* sigma_next, void* out, int32_t nsamples, int64_t per_sample, void* stream) {
+  if (!x || !den || !x_euler || !den2 || !sigma_hat || !sigma_next || !out || nsamples <= 0 || per_sample <= 0) {
+    set_error("v3d_heun_step: bad args");
+    return V3D_ERR_BAD_ARG;
+  }
+  heun_step_kernel<<<ew_blocks(nsamples * per_sample), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<const float*>(den), static_cast<const float*>(x_euler),
+      static_cast<const float*>(den2), static_cast<const float*>(sigma_hat), static_cast<const float*>(sigma_next),
+      static_cast<float*>(out), nsamples, per_sample);
+  V3D_CHECK_LAUNCH("heun_step_kernel");
   return V3D_OK;
 }
 

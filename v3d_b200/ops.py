@@ -291,6 +291,16 @@ def euler_step(x, den, sigma_hat, sigma_next, out, nsamples: int, per_sample: in
     return out
 
 
+def heun_step(x, den, x_euler, den2, sigma_hat, sigma_next, out, nsamples: int, per_sample: int):
+    for t, name in ((x, "x"), (den, "den"), (x_euler, "x_euler"), (den2, "den2"), (sigma_hat, "sigma_hat"),
+                    (sigma_next, "sigma_next"), (out, "out")):
+        _need(t, torch.float32, "heun_step " + name)
+    _lib.check(_lib.load().v3d_heun_step(x.data_ptr(), den.data_ptr(), x_euler.data_ptr(), den2.data_ptr(),
+                                         sigma_hat.data_ptr(), sigma_next.data_ptr(), out.data_ptr(), nsamples,
+                                         per_sample, _stream()), "v3d_heun_step")
+    return out
+
+
 def decode_to_u8(x: torch.Tensor, ldx: int, y: torch.Tensor, npix: int):
     _lib.check(_lib.load().v3d_decode_to_u8(x.data_ptr(), ldx, 1 if x.dtype == torch.float32 else 0,
                                             y.data_ptr(), npix, _stream()), "v3d_decode_to_u8")

@@ -1,7 +1,9 @@
 """Sampling-side drop-ins for the sgm plugin surface (reference sgm/modules/diffusionmodules/):
 `EDMDiscretization` (discretizer.py:18-39), `LinearPredictionGuider` (guiders.py:60-101),
 `VScalingWithEDMcNoise` + `Denoiser` (denoiser_scaling.py:51-59, denoiser.py:12-39), `OpenAIWrapper`
-(wrappers.py:9-34) and `EulerEDMSampler` (sampling.py:24-133,214-218).
+(wrappers.py:9-34), `EulerEDMSampler` (sampling.py:24-133,214-218) and - SURVEY 8(f)-3, same denoiser, no new
+tensor-core work - `HeunEDMSampler` (sampling.py:221-237), `VanillaCFG` (guiders.py:23-42) and
+`CentralPredictionGuider` (guiders.py:104-146).
 
 Call shapes are the reference's: `sampler(denoiser, x, cond=c, uc=uc) -> x`, `denoiser(network, input, sigma,
 cond, **kw)`, `network(x, t, c, **kw)`; any denoiser closure works (scripts/pub/V3D_512.py:278-283).  The
@@ -51,13 +53,14 @@ class EDMDiscretization:
         return sigmas if not flip else torch.flip(sigmas, (0,))
 
 
-class LinearPredictionGuider:
-    """Per-frame CFG scale linspace(min, max, T); batch order [uc; c] (guiders.py:60-101)."""
+class _FrameScaleGuider:
+    """Shared machinery of the classifier-free guiders: batch order [uc; c], `x_u + scale_t (x_c - x_u)` with one
+    scale per frame of a video (`self.scale`, shape [1, T]); the combine runs in v3d_cfg_combine."""
 
-    def __init__(self, max_scale: float, num_frames: int, min_scale: float = 1.0,
-                 additional_cond_keys: Optional[Union[List[str], str]] = None):
-        self.min_scale, self.max_scale, self.num_frames = min_scale, max_scale, num_frames
-        self.scale = torch.linspace(min_scale, max_scale, num_frames, device="cpu").unsqueeze(0)
+    additional_cond_keys: List[str] = []
+    num_frames: int = 1
+
+    def _init_keys(self, additional_cond_keys) -> None:
         if additional_cond_keys is None:
             additional_cond_keys = []
         if isinstance(additional_cond_keys, str):
@@ -93,6 +96,54 @@ class LinearPredictionGuider:
                 assert c[k] == uc[k]
                 c_out[k] = c[k]
         return torch.cat([x] * 2), torch.cat([s] * 2), c_out
+
+
+class LinearPredictionGuider(_FrameScaleGuider):
+    """Per-frame CFG scale linspace(min, max, T); batch order [uc; c] (guiders.py:60-101)."""
+
+    def __init__(self, max_scale: float, num_frames: int, min_scale: float = 1.0,
+                 additional_cond_keys: Optional[Union[List[str], str]] = None):
+        self.min_scale, self.max_scale, self.num_frames = min_scale, max_scale, num_frames
+        self.scale = torch.linspace(min_scale, max_scale, num_frames, device="cpu").unsqueeze(0)
+        self._init_keys(additional_cond_keys)
+
+
+class CentralPredictionGuider(_FrameScaleGuider):
+    """Triangular per-frame scale: linspace(min, 2 max, T) mirrored about the middle frame (guiders.py:104-146)."""
+
+    def __init__(self, max_scale: float, num_frames: int, min_scale: float = 1.0,
+                 additional_cond_keys: Optional[Union[List[str], str]] = None):
+        self.min_scale, self.max_scale, self.num_frames = min_scale, max_scale, num_frames
+        scale = torch.linspace(min_scale, 2 * max_scale, num_frames, device="cpu")
+        scale[num_frames // 2:] = 2 * max_scale - scale[num_frames // 2:]
+        self.scale = scale.unsqueeze(0)
+        self._init_keys(additional_cond_keys)
+
+
+class VanillaCFG(_FrameScaleGuider):
+    """One scale for every sample: `x_u + scale (x_c - x_u)` (guiders.py:23-42)."""
+
+    def __init__(self, scale: float):
+        self.num_frames = 1
+        self.scale_value = float(scale)
+        self._init_keys(None)
+
+    # the reference keeps a python float in `.scale`; the device copy is derived from it on use
+    @property
+    def scale(self):
+        return self._scale_t
+
+    @scale.setter
+    def scale(self, v):
+        self._scale_t = v if isinstance(v, torch.Tensor) else torch.tensor([[float(v)]])
+
+    @property
+    def scale_value(self) -> float:
+        return float(self._scale_t.reshape(-1)[0])
+
+    @scale_value.setter
+    def scale_value(self, v: float) -> None:
+        self.scale = v
 
 
 class VScalingWithEDMcNoise:
@@ -226,3 +277,49 @@ class EulerEDMSampler:
             gamma = min(self.s_churn / (num_sigmas - 1), 2 ** 0.5 - 1) if self.s_tmin <= host[i] <= self.s_tmax else 0.0
             x = self.sampler_step(sig_rows[i], sig_rows[i + 1], denoiser, x, cond, uc, gamma)
         return x
+
+
+class HeunEDMSampler(EulerEDMSampler):
+    """Second-order EDM sampler (sampling.py:221-237): after the Euler proposal the denoiser is evaluated once more at
+    sigma_next and the step is redone with the averaged slope; the last step (sigma_next = 0) stays first order, which
+    also saves the network evaluation exactly as the reference does (`torch.sum(next_sigma) < 1e-14`)."""
+
+    _next_sigma_host: Optional[float] = None  # set by __call__: lets the step skip the device->host sync
+
+    def sampler_step(self, sigma, next_sigma, denoiser, x, cond, uc=None, gamma: float = 0.0):
+        sigma_hat = sigma if gamma == 0 else sigma * (gamma + 1.0)
+        if gamma > 0:
+            eps = torch.randn_like(x) * self.s_noise
+            x = x + eps * (sigma_hat ** 2 - sigma ** 2).reshape(-1, *([1] * (x.ndim - 1))) ** 0.5
+        n, per = x.shape[0], x[0].numel()
+        denoised = self.denoise(x, denoiser, sigma_hat, cond, uc).float().contiguous()
+        x_euler = torch.empty_like(x)
+        ops.euler_step(x, denoised, sigma_hat, next_sigma, x_euler, n, per)
+        nsum = self._next_sigma_host if self._next_sigma_host is not None else float(next_sigma.sum())
+        if nsum < 1e-14:
+            return x_euler
+        denoised2 = self.denoise(x_euler, denoiser, next_sigma, cond, uc).float().contiguous()
+        out = torch.empty_like(x)
+        ops.heun_step(x, denoised, x_euler, denoised2, sigma_hat.float().contiguous(),
+                      next_sigma.float().contiguous(), out, n, per)
+        return out
+
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
+        if not x.is_cuda:
+            raise RuntimeError("v3d_b200.HeunEDMSampler needs CUDA tensors; there is no CPU fallback")
+        assert x.dtype == torch.float32, "sampler state is fp32 (denoiser.py:36-39)"
+        x, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        n = x.shape[0]
+        sig_rows = sigmas.float().reshape(-1, 1).expand(num_sigmas, n).contiguous().to(x.device)
+        host = [float(s) for s in sigmas]
+        x = x.contiguous()
+        try:
+            for i in range(num_sigmas - 1):
+                gamma = (min(self.s_churn / (num_sigmas - 1), 2 ** 0.5 - 1)
+                         if self.s_tmin <= host[i] <= self.s_tmax else 0.0)
+                self._next_sigma_host = host[i + 1] * n
+                x = self.sampler_step(sig_rows[i], sig_rows[i + 1], denoiser, x, cond, uc, gamma)
+        finally:
+            self._next_sigma_host = None
+        return x
+
