@@ -6,6 +6,7 @@ parity against the reference modules lives in test_parity_gpu.py with committed 
 Tolerances: outputs are bf16 (8 mantissa bits) -> |err| <= 2^-8 * |ref| + small absolute slack, stated per test.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -380,3 +381,41 @@ def test_sampler_arithmetic_and_u8():
     ops.decode_to_u8(img, 16, u8, 100)
     ref = (torch.clamp((img[:, :3] + 1.0) / 2.0, 0.0, 1.0) * 255).to(torch.uint8)
     assert (u8.int() - ref.int()).abs().max() <= 1  # fp rounding of the *255 product may differ by one ulp
+
+
+# ---- not yet seen on hardware (written after the round-1 GPU budget was spent): enabled with V3D_RUN_UNVALIDATED=1
+_unvalidated = pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
+                                  reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")
+
+
+@_unvalidated
+def test_heun_step_kernel():
+    """v3d_heun_step vs the formula of HeunEDMSampler.possible_correction_step (sampling.py:221-237)."""
+    n, per = 6, 4 * 16 * 16
+    x, den, den2 = (torch.randn(n, per, device=DEV) for _ in range(3))
+    sh = torch.rand(n, device=DEV) * 5 + 1.0
+    sn = sh * 0.5
+    sn[-2:] = 0.0  # samples whose next sigma is 0 keep the Euler proposal
+    xe = torch.empty_like(x)
+    ops.euler_step(x, den, sh, sn, xe, n, per)
+    out = torch.empty_like(x)
+    ops.heun_step(x, den, xe, den2, sh, sn, out, n, per)
+    d = (x - den) / sh[:, None]
+    dt = (sn - sh)[:, None]
+    d2 = (xe - den2) / sn.clamp_min(1e-30)[:, None]
+    ref = torch.where(sn[:, None] > 0, x + (d + d2) / 2 * dt, x + dt * d)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+@_unvalidated
+def test_gemm_cta_pair_path_subprocess():
+    """The cta_group::2 (CTA pair) GEMM tiles are opt-in (V3D_GEMM_2CTA=1, read once per process): re-run the GEMM /
+    conv tests of this file in a child process with the switch on, under a hard timeout."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, V3D_GEMM_2CTA="1", V3D_RUN_UNVALIDATED="0")
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
+                          "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+

@@ -55,10 +55,12 @@ struct GemmEpi {
 #define V3D_DBG(bit) (0)
 #endif
 
-template <int BN>
+// NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile;
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader's tensor core reads both halves.
+template <int BN, int NCTA = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 8 * 4096;  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled
   static constexpr int NSTAGE_RAW = (kSmemBudget - 2048 - STAGING_BYTES) / STAGE_BYTES;
@@ -78,15 +80,16 @@ constexpr int EPI_GEGLU = 1;  // value * gelu(gate) then as EPI_BF16 (linear mod
 constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
 
-// Persistent tile walk without per-tile divisions: tile = blockIdx.x + i * gridDim.x, n fastest.
+// Persistent tile walk without per-tile divisions: tile = first + i * step, n fastest.  With CTA pairs the walk is
+// over pair tiles (m_tile = pair index; the CTA's own 128-row tile is 2 * m_tile + rank).
 struct TileWalk {
   int n_tile, m_tile, step_n, step_m, num_n;
-  __device__ __forceinline__ explicit TileWalk(const GemmEpi& p) {
+  __device__ __forceinline__ TileWalk(const GemmEpi& p, int ncta) {
     num_n = p.num_n_tiles;
-    n_tile = static_cast<int>(blockIdx.x) % num_n;
-    m_tile = static_cast<int>(blockIdx.x) / num_n;
-    step_n = static_cast<int>(gridDim.x) % num_n;
-    step_m = static_cast<int>(gridDim.x) / num_n;
+    n_tile = (static_cast<int>(blockIdx.x) / ncta) % num_n;
+    m_tile = (static_cast<int>(blockIdx.x) / ncta) / num_n;
+    step_n = (static_cast<int>(gridDim.x) / ncta) % num_n;
+    step_m = (static_cast<int>(gridDim.x) / ncta) / num_n;
   }
   __device__ __forceinline__ void next() {
     n_tile += step_n;
@@ -127,11 +130,12 @@ __device__ __forceinline__ void tile_origin(const GemmEpi& p, int m_tile, int& t
   }
 }
 
-template <int BN, bool CONV, int EPI>
+template <int BN, bool CONV, int EPI, int NCTA = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapD, const GemmEpi p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NCTA>;
+  static_assert(NCTA == 1 || NCTA == 2, "one CTA or a CTA pair");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -155,20 +159,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int i = 0; i < C::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 8 * NCTA);  // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  // rank inside the pair; the persistent walk is over pair tiles: first = blockIdx.x / NCTA, step = gridDim.x / NCTA
+  const int cta_rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int total_tiles = ((p.num_m_tiles + NCTA - 1) / NCTA) * p.num_n_tiles;
   const int num_kb = p.ntaps * p.kpt;
 
   if (warp == 0) {
@@ -177,14 +189,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int tr_n = 0;
-      TileWalk tw(p);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next()) {
+      TileWalk tw(p, NCTA);
+      for (int tile = blockIdx.x / NCTA; tile < total_tiles; tile += gridDim.x / NCTA, tw.next()) {
         const int n_tile = tw.n_tile;
+        const int m_tile = tw.m_tile * NCTA + cta_rank;
         int c1, c2, c3;
         if (CONV) {
-          tile_origin<true>(p, tw.m_tile, c1, c2, c3);
+          tile_origin<true>(p, m_tile, c1, c2, c3);
         } else {
-          tile_origin<false>(p, tw.m_tile, c2, c1, c3);
+          tile_origin<false>(p, m_tile, c2, c1, c3);
         }
         const int bz = p.b_batched ? c2 : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -192,17 +205,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (V3D_DIAG(p.trace && blockIdx.x == 0 && tr_n < 1024)) p.trace[tr_n++] = clock64();
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          // pair: only the leader arms its barrier, with the bytes of both CTAs; the peer's loads credit it remotely
+          if (NCTA == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], NCTA * C::STAGE_BYTES);
           const int tap = kb / p.kpt;
           const int kc = (kb - tap * p.kpt) * BK;
-          if (CONV) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
+          if (NCTA == 2) {
+            if (CONV) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_2cta(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
+            } else {
+              tma_load_3d_2cta(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift, c2);
+            }
+            // this CTA's half of the B tile: rows [rank * BN/2, (rank + 1) * BN/2) of the N tile
+            tma_load_3d_2cta(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN + cta_rank * (BN / 2), bz);
           } else {
-            tma_load_3d(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift,
-                        c2);
+            if (CONV) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
+            } else {
+              tma_load_3d(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift,
+                          c2);
+            }
+            tma_load_3d(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN, bz);
           }
-          tma_load_3d(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN, bz);
           if (++stage == C::NSTAGE) {
             stage = 0;
             phase ^= 1u;
@@ -212,14 +237,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && (NCTA == 1 || cta_rank == 0)) {  // pair: the leader issues for both SMs
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int tr_m = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x / NCTA; tile < total_tiles; tile += gridDim.x / NCTA) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         if (V3D_DIAG(p.trace && blockIdx.x == 0 && tr_m < 1020)) p.trace[1024 + tr_m++] = -clock64();  // negative: tile start
@@ -234,16 +259,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per 16-element K step inside the 128B swizzle atom (encoded >>4)
-            tc_mma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NCTA == 2)
+              tc_mma_f16_2cta(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              tc_mma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                         idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if (NCTA == 2) tc_commit_2cta(&empty_bar[stage], 3);  // frees the stage in both CTAs
+          else tc_commit(&empty_bar[stage]);
           if (++stage == C::NSTAGE) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tfull_bar[acc]);
+        if (NCTA == 2) tc_commit_2cta(&tfull_bar[acc], 3);  // each CTA's epilogue reads its own 128 rows
+        else tc_commit(&tfull_bar[acc]);
         if (++acc == C::ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1u;
@@ -310,13 +341,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         return m < p.rows_per_batch;
       }
     };
-    TileWalk tw(p);
+    TileWalk tw(p, NCTA);
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = blockIdx.x / NCTA; tile < total_tiles; tile += gridDim.x / NCTA, ++iter) {
       V3D_ETRACE();  // [0] tile prologue start
       const int n_tile = tw.n_tile;
       int t0, t1, t2;
-      tile_origin<CONV>(p, tw.m_tile, t0, t1, t2);
+      tile_origin<CONV>(p, tw.m_tile * NCTA + cta_rank, t0, t1, t2);
       tw.next();  // tw now names the next tile (used by the residual prefetch below)
       // with an odd number of sub-tiles the two groups swap the larger share every tile, so neither paces the other
       const int hsel = (NSUB & 1) ? (half ^ (iter & 1)) : half;
@@ -391,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // come from HBM); the first iteration also covers the next tile
         auto prefetch_tile = [&](const TileWalk& w, int cb) {
           int u0, u1, u2;
-          tile_origin<CONV>(p, w.m_tile, u0, u1, u2);
+          tile_origin<CONV>(p, w.m_tile * NCTA + cta_rank, u0, u1, u2);
           long long nrow;
           if (map_row(u0, u1, u2, nrow)) {
             const int ncol0 = w.n_tile * OUT_COLS + cb * 16;
@@ -402,7 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
         };
-        const int step = static_cast<int>(gridDim.x);
+        const int step = static_cast<int>(gridDim.x) / NCTA;
         if (iter == 0 && tile + step < total_tiles) prefetch_tile(tw, c_begin_next);
         if (tile + 2 * step < total_tiles) {
           TileWalk tw2 = tw;
@@ -583,7 +614,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       V3D_ETRACE();  // tile done
       if (++acc == C::ACC_STAGES) {
         acc = 0;
@@ -596,9 +630,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the peer's shared memory and TMEM stay alive until the leader's MMAs retired
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -616,12 +652,12 @@ static int pick_block_n(int N, int act) {
   return 0;
 }
 
-template <int BN, bool CONV, int EPI>
+template <int BN, bool CONV, int EPI, int NCTA = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmEpi& epi,
                   cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NCTA>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, CONV, EPI>;
+  auto kern = gemm_tc_kernel<BN, CONV, EPI, NCTA>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -630,11 +666,52 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     }
     configured = true;
   }
-  const int total = epi.num_m_tiles * epi.num_n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi);
+  if (NCTA == 1) {
+    const int total = epi.num_m_tiles * epi.num_n_tiles;
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi);
+  } else {
+    // one cluster of two CTAs per 256-row pair tile, persistent over at most num_sms / 2 clusters
+    const int total = ((epi.num_m_tiles + 1) / 2) * epi.num_n_tiles;
+    const int clusters = total < num_sms() / 2 ? total : num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, epi);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc_kernel (CTA pair) launch failed: %s", cudaGetErrorString(e));
+      return V3D_ERR_CUDA;
+    }
+  }
   V3D_CHECK_LAUNCH("gemm_tc_kernel");
   return V3D_OK;
+}
+
+// CTA-pair variants exist for the wide bf16-output tiles only (the shapes that are ingest-bound with one CTA)
+template <int BN, bool CONV>
+static int dispatch_epi_pair(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                             const GemmEpi& epi, cudaStream_t st) {
+  if constexpr (BN == 160 || BN == 256) {
+    switch (epi_kind) {
+      case EPI_BF16: return launch<BN, CONV, EPI_BF16, 2>(ma, mb, md, epi, st);
+      case EPI_BF16R2: return launch<BN, CONV, EPI_BF16R2, 2>(ma, mb, md, epi, st);
+      case EPI_GEGLU:
+        if constexpr (!CONV && BN == 256) return launch<256, false, EPI_GEGLU, 2>(ma, mb, md, epi, st);
+        break;
+    }
+  }
+  set_error("no CTA-pair variant for epilogue %d / block_n %d", epi_kind, BN);
+  return V3D_ERR_BAD_ARG;
 }
 
 template <int BN, bool CONV>
@@ -657,7 +734,14 @@ static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& 
 
 template <bool CONV>
 static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                       const GemmEpi& epi, cudaStream_t st) {
+                       const GemmEpi& epi, cudaStream_t st, bool pair = false) {
+  if (pair) {
+    switch (bn) {
+      case 256: return dispatch_epi_pair<256, CONV>(epi_kind, ma, mb, md, epi, st);
+      case 160: return dispatch_epi_pair<160, CONV>(epi_kind, ma, mb, md, epi, st);
+      default: set_error("no CTA-pair variant for block_n %d", bn); return V3D_ERR_BAD_ARG;
+    }
+  }
   switch (bn) {
     case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, md, epi, st);
     case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, md, epi, st);
@@ -880,12 +964,24 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       e.b_batched = 1;
     }
   }
+  // CTA-pair (cta_group::2) tiles: opt-in (V3D_GEMM_2CTA=1) until validated on hardware; wide bf16-output tiles only
+  bool pair = false;
+  {
+    static int want_pair = -1;
+    if (want_pair < 0) {
+      const char* v = getenv("V3D_GEMM_2CTA");
+      want_pair = (v && atoi(v) != 0) ? 1 : 0;
+    }
+    const bool staged_out = !a->out_transposed && !a->out_fp32;
+    pair = want_pair == 1 && staged_out && e.num_m_tiles >= 2 &&
+           (bn == 256 || (bn == 160 && a->act != V3D_ACT_GEGLU));
+  }
   {
     const uint64_t ktot = (uint64_t)ntaps * a->K;
     const uint64_t bbs = b_batch > 1 ? (uint64_t)a->b_batch_stride : (uint64_t)a->N * a->ldb;
     const uint64_t dims[3] = {ktot, (uint64_t)a->N, (uint64_t)b_batch};
     const uint64_t str[2] = {(uint64_t)a->ldb * 2, bbs * 2};
-    const uint32_t box[3] = {BK, (uint32_t)bn, 1};
+    const uint32_t box[3] = {BK, (uint32_t)(pair ? bn / 2 : bn), 1};  // a pair stages half of the B tile per CTA
     rc = make_tmap_bf16(&mb, a->B, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -923,5 +1019,6 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     }
     if (rc) return rc;
   }
-  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st) : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st);
+  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st, pair)
+              : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st, pair);
 }
