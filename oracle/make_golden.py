@@ -10,6 +10,7 @@ unless they agree to <= 2e-4 of the output scale.  Only the reference's outputs 
 """
 from __future__ import annotations
 
+import importlib
 import json
 import sys
 import time
@@ -17,7 +18,7 @@ from pathlib import Path
 
 import torch
 
-from . import ref_decoder, ref_sampling, ref_unet, reference_shim, synth
+from . import ref_decoder, ref_encoder, ref_sampling, ref_unet, reference_shim, synth
 
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 PIN_TOL = 2e-4
@@ -159,6 +160,33 @@ def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, ma
                          ref_cpu_seconds=round(t_ref, 2), out_std=ref.std().item())
 
 
+def _encoder_case(ns, tag: str, ch: int, B: int, hw: int, wseed: int, manifest: dict):
+    """the first-stage ENCODE front-end (configs/ae/video.yaml encoder + DiagonalGaussianDistribution)."""
+    enc = ns.model.Encoder(attn_type="vanilla", double_z=True, z_channels=4, resolution=hw, in_channels=3, out_ch=3,
+                           ch=ch, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0).eval()
+    spec = ref_encoder.EncoderSpec(ch=ch)
+    shapes = ref_encoder.encoder_param_shapes(spec)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+    sd = synth.synth_state_dict(shapes, seed=wseed)
+    enc.load_state_dict(sd)
+    g = torch.Generator().manual_seed(78)
+    x = torch.rand(B, 3, hw, hw, generator=g) * 2.0 - 1.0   # images are scaled to [-1, 1] (autoencoder.py:171-175)
+    noise = torch.randn(B, 4, hw // 8, hw // 8, generator=g)
+    dist = importlib.import_module("sgm.modules.distributions.distributions")
+    with torch.no_grad():
+        ref = enc(x)
+        ora = ref_encoder.encoder_forward(sd, spec, x)
+        post = dist.DiagonalGaussianDistribution(ref)
+        ref_z = post.mean + post.std * noise          # .sample() with the normal draw made explicit
+        ora_z = ref_encoder.gaussian_sample(ora, noise)
+        assert torch.equal(post.mode(), ref_encoder.gaussian_mode(ref))
+    err = _pin(tag, ref, ora)
+    _pin(tag + ":sample", ref_z, ora_z)
+    torch.save({"x": x, "noise": noise, "moments": ref, "z": ref_z}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="encode", ch=ch, B=B, image_hw=hw, weight_seed=wseed, x_seed=78, pin_err=err,
+                         out_std=ref.std().item())
+
+
 def main(argv):
     OUT.mkdir(parents=True, exist_ok=True)
     ns = reference_shim.load()
@@ -192,6 +220,10 @@ def main(argv):
         _decoder_case(ns, "decoder_small_2videos", 64, T=2, B=4, hw=8, wseed=5, manifest=manifest)
     if want("decoder_full"):
         _decoder_case(ns, "decoder_full", 128, T=2, B=2, hw=16, wseed=6, manifest=manifest)
+    if want("encoder_small"):
+        _encoder_case(ns, "encoder_small", 64, B=2, hw=64, wseed=7, manifest=manifest)
+    if want("encoder_full"):
+        _encoder_case(ns, "encoder_full", 128, B=1, hw=128, wseed=8, manifest=manifest)
     # integer / index paths: sigma schedule and guider scale, bit-exact
     if want("schedule"):
         disc = ns.discretizer.EDMDiscretization(sigma_max=700.0)

@@ -164,6 +164,42 @@ def test_other_guiders_host_logic_bit_exact():
         smp(lambda *a: None, torch.randn(2, 4, 8, 8), cond={}, uc={})
 
 
+def test_encoder_state_dict_layout_and_engine_opt_in():
+    """Native Encoder: reference state_dict layout (106 tensors, configs/ae/video.yaml); the engine builds it only
+    when encoder_config.target names this package's class, and its Gaussian regulariser follows distributions.py."""
+    from oracle import ref_encoder
+    from v3d_b200.decoder import AutoencodingEngine
+    from v3d_b200.encoder import DiagonalGaussianRegularizer, Encoder
+
+    kw = dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64,
+              ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    enc = Encoder(**kw)
+    want = ref_encoder.encoder_param_shapes(ref_encoder.EncoderSpec(ch=64))
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v) for k, v in want.items()}
+    assert len(want) == 106
+    with pytest.raises(NotImplementedError):
+        Encoder(**dict(kw, attn_resolutions=[32]))
+    dkw = dict(kw, video_kernel_size=[3, 1, 1])
+    ref_target = {"target": "sgm.modules.diffusionmodules.model.Encoder", "params": kw}
+    ae = AutoencodingEngine(decoder_config={"params": dkw}, encoder_config=ref_target)
+    assert ae.encoder is None
+    with pytest.raises(NotImplementedError):
+        ae.encode(torch.zeros(1, 3, 64, 64))
+    ae = AutoencodingEngine(decoder_config={"params": dkw},
+                            encoder_config={"target": "v3d_b200.sgm.modules.diffusionmodules.model.Encoder", "params": kw},
+                            regularizer_config={"target": "x.DiagonalGaussianRegularizer"})
+    assert sum(k.startswith("encoder.") for k in ae.state_dict()) == 106
+    with pytest.raises(RuntimeError):           # CUDA only, no CPU fallback
+        ae.encode(torch.zeros(1, 3, 64, 64))
+    mom = torch.randn(2, 8, 4, 4)
+    mom[:, 4:] = mom[:, 4:] * 30.0               # exercises the logvar clamp
+    noise = torch.randn(2, 4, 4, 4)
+    z, _ = DiagonalGaussianRegularizer(sample=True)(mom, noise=noise)
+    assert torch.equal(z, ref_encoder.gaussian_sample(mom, noise))
+    z, _ = DiagonalGaussianRegularizer(sample=False)(mom)
+    assert torch.equal(z, mom[:, :4])
+
+
 def test_drop_in_targets_resolve():
     from v3d_b200.sampling import get_obj_from_str
 
@@ -178,6 +214,8 @@ def test_drop_in_targets_resolve():
                        "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
                        "sgm.modules.diffusionmodules.wrappers.OpenAIWrapper",
                        "sgm.modules.autoencoding.temporal_ae.VideoDecoder",
+                       "sgm.modules.diffusionmodules.model.Encoder",
+                       "sgm.modules.autoencoding.regularizers.DiagonalGaussianRegularizer",
                        "sgm.models.autoencoder.AutoencodingEngine",
                        "sgm.models.video_diffusion.DiffusionEngine"]:
         assert get_obj_from_str("v3d_b200." + ref_target) is not None

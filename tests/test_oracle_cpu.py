@@ -6,7 +6,7 @@ from pathlib import Path
 import pytest
 import torch
 
-from oracle import ref_decoder, ref_sampling, ref_unet, synth
+from oracle import ref_decoder, ref_encoder, ref_sampling, ref_unet, synth
 
 GOLD = Path(__file__).resolve().parent / "golden"
 MANIFEST = json.loads((GOLD / "MANIFEST.json").read_text())
@@ -85,6 +85,21 @@ def test_oracle_decoder_vs_reference_golden(tag):
     with torch.no_grad():
         out = ref_decoder.decoder_forward(sd, spec, gold["z"] / 0.18215, m["T"])
     assert _close(out, gold["out"])
+
+
+@pytest.mark.parametrize("tag", ["encoder_small", "encoder_full"])
+def test_oracle_encoder_vs_reference_golden(tag):
+    """Encoder.forward + DiagonalGaussianDistribution.sample (noise explicit) vs the real reference."""
+    m = MANIFEST[tag]
+    gold = torch.load(GOLD / f"{tag}.pt")
+    spec = ref_encoder.EncoderSpec(ch=m["ch"])
+    sd = synth.synth_state_dict(ref_encoder.encoder_param_shapes(spec), seed=m["weight_seed"])
+    with torch.no_grad():
+        mom = ref_encoder.encoder_forward(sd, spec, gold["x"])
+    assert tuple(mom.shape) == (m["B"], 8, m["image_hw"] // 8, m["image_hw"] // 8)
+    assert _close(mom, gold["moments"])
+    assert _close(ref_encoder.gaussian_sample(mom, gold["noise"]), gold["z"])
+    assert torch.equal(ref_encoder.gaussian_mode(gold["moments"]), gold["moments"][:, :4])
 
 
 def test_oracle_schedule_bit_exact():

@@ -305,10 +305,13 @@ class VideoDecoder(KernelModule):
 
 
 class AutoencodingEngine(nn.Module):
-    """Decode-side drop-in for `sgm.models.autoencoder.AutoencodingEngine` (autoencoder.py:128-212).
+    """Drop-in for `sgm.models.autoencoder.AutoencodingEngine` (autoencoder.py:128-212).
 
-    Only `decoder_config` is built natively (the encoder runs once per image and is SURVEY.md §8(f) rank 1);
-    state_dict keys keep the `decoder.` prefix so `first_stage_model.decoder.*` checkpoints load unchanged.
+    `decoder_config` is always built natively; state_dict keys keep the `decoder.` prefix so
+    `first_stage_model.decoder.*` checkpoints load unchanged.  The encode side (once per image)
+    is built natively only when `encoder_config.target` names this package's Encoder
+    (`v3d_b200.sgm.modules.diffusionmodules.model.Encoder`); with the reference's target it stays decode-only, as
+    scripts/pub/V3D_512.py:145-162 encodes with a separately loaded `ae_model`.
     """
 
     def __init__(self, *args, decoder_config: Optional[dict] = None, encoder_config=None, loss_config=None,
@@ -317,9 +320,26 @@ class AutoencodingEngine(nn.Module):
         assert decoder_config is not None
         params = dict(decoder_config.get("params", dict())) if hasattr(decoder_config, "get") else dict(decoder_config)
         self.decoder = VideoDecoder(**params)
+        self.encoder = None
+        self.regularization = None
+        target = str(encoder_config.get("target", "")) if hasattr(encoder_config, "get") else ""
+        if target.startswith("v3d_b200."):
+            from .encoder import DiagonalGaussianRegularizer, Encoder
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("the VAE encoder is not part of the B200 hot path (SURVEY.md §8(f))")
+            self.encoder = Encoder(**dict(encoder_config.get("params", dict())))
+            rparams = dict(regularizer_config.get("params", dict())) if hasattr(regularizer_config, "get") else {}
+            self.regularization = DiagonalGaussianRegularizer(**rparams)
+
+    def encode(self, x: torch.Tensor, return_reg_log: bool = False, unregularized: bool = False):
+        """autoencoder.py:196-208: z = encoder(x); (z, log) = regularization(z)."""
+        if self.encoder is None:
+            raise NotImplementedError("this AutoencodingEngine was built decode-only; point encoder_config.target at "
+                                      "v3d_b200.sgm.modules.diffusionmodules.model.Encoder to build the native encoder")
+        z = self.encoder(x)
+        if unregularized:
+            return z, dict()
+        z, reg_log = self.regularization(z)
+        return (z, reg_log) if return_reg_log else z
 
     def decode(self, z: torch.Tensor, **kwargs) -> torch.Tensor:
         return self.decoder(z, **kwargs)
