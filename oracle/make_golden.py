@@ -18,7 +18,7 @@ from pathlib import Path
 
 import torch
 
-from . import ref_decoder, ref_encoder, ref_sampling, ref_unet, reference_shim, synth
+from . import ref_conditioning, ref_decoder, ref_encoder, ref_sampling, ref_unet, reference_shim, synth
 
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 PIN_TOL = 2e-4
@@ -187,6 +187,43 @@ def _encoder_case(ns, tag: str, ch: int, B: int, hw: int, wseed: int, manifest: 
                          out_std=ref.std().item())
 
 
+def _conditioning_case(ns, tag: str, T: int, hw: int, manifest: dict):
+    """(c, uc) of scripts/pub/V3D_512.py:247-262 through the real GeneralConditioner with the embedder
+    list of scripts/pub/configs/V3D_512.yaml:59-86.  get_batch (V3D_512.py:31-69) lives in a script that cannot be
+    imported offline (it loads CLIP); its five assignments are restated below."""
+    reference_shim._stub("kornia")
+    reference_shim._stub("open_clip")
+    mods = importlib.import_module("sgm.modules.encoders.modules")
+    base = "sgm.modules.encoders.modules."
+    emb = lambda key, target, **p: dict(input_key=key, is_trainable=False, target=base + target, params=p)  # noqa: E731
+    cond = mods.GeneralConditioner([
+        dict(emb("cond_frames_without_noise", "IdentityEncoder"), ucg_rate=0.2),
+        emb("fps_id", "ConcatTimestepEmbedderND", outdim=256),
+        emb("motion_bucket_id", "ConcatTimestepEmbedderND", outdim=256),
+        dict(emb("cond_frames", "IdentityEncoder"), ucg_rate=0.2),
+        emb("cond_aug", "ConcatTimestepEmbedderND", outdim=256)]).eval()
+    g = torch.Generator().manual_seed(79)
+    clip_emb = torch.randn(1, 1, 1024, generator=g)
+    latent = torch.randn(1, 4, hw, hw, generator=g)
+    fps_id, motion, aug = 6.0, 127.0, 0.02
+    batch = {"fps_id": torch.tensor([fps_id]).repeat(T), "motion_bucket_id": torch.tensor([motion]).repeat(T),
+             "cond_aug": torch.tensor([aug]).repeat(T), "cond_frames": latent.clone(),
+             "cond_frames_without_noise": clip_emb.clone(), "num_video_frames": T}
+    batch_uc = {k: v.clone() for k, v in batch.items() if isinstance(v, torch.Tensor)}
+    with torch.no_grad():
+        c, uc = cond.get_unconditional_conditioning(
+            batch, batch_uc=batch_uc, force_uc_zero_embeddings=["cond_frames", "cond_frames_without_noise"])
+    for d in (c, uc):
+        for k in ("crossattn", "concat"):
+            d[k] = d[k].unsqueeze(1).expand(d[k].shape[0], T, *d[k].shape[1:]).reshape(-1, *d[k].shape[1:]).clone()
+    oc, ouc = ref_conditioning.v3d_conditioning(clip_emb, latent, fps_id, motion, aug, T)
+    for k in ("vector", "crossattn", "concat"):
+        assert torch.equal(c[k], oc[k]) and torch.equal(uc[k], ouc[k]), k
+    print(f"  pin {tag}: vector / crossattn / concat bit-exact")
+    torch.save({"clip_emb": clip_emb, "latent": latent, "c": c, "uc": uc}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="conditioning", T=T, latent_hw=hw, fps_id=fps_id, motion_bucket_id=motion, cond_aug=aug)
+
+
 def main(argv):
     OUT.mkdir(parents=True, exist_ok=True)
     ns = reference_shim.load()
@@ -224,6 +261,8 @@ def main(argv):
         _encoder_case(ns, "encoder_small", 64, B=2, hw=64, wseed=7, manifest=manifest)
     if want("encoder_full"):
         _encoder_case(ns, "encoder_full", 128, B=1, hw=128, wseed=8, manifest=manifest)
+    if want("conditioning"):
+        _conditioning_case(ns, "conditioning", T=18, hw=8, manifest=manifest)
     # integer / index paths: sigma schedule and guider scale, bit-exact
     if want("schedule"):
         disc = ns.discretizer.EDMDiscretization(sigma_max=700.0)

@@ -200,6 +200,26 @@ def test_encoder_state_dict_layout_and_engine_opt_in():
     assert torch.equal(z, mom[:, :4])
 
 
+def test_conditioning_assembly_matches_reference_golden(monkeypatch):
+    """GeneralConditioner / get_batch / per-frame repeat logic vs the real reference's (c, uc) (bit-exact).  The
+    sinusoidal embedding itself is a CUDA kernel; here it is swapped for the oracle's so the HOST logic (key routing,
+    concat order, uc zeroing, repeats) runs on CPU."""
+    from pathlib import Path
+
+    from oracle import ref_conditioning
+    from v3d_b200 import conditioning
+
+    gold = torch.load(Path(__file__).resolve().parent / "golden" / "conditioning.pt")
+    monkeypatch.setattr(conditioning.ConcatTimestepEmbedderND, "forward",
+                        lambda self, x: ref_conditioning.concat_timestep_embed(x, self.outdim))
+    cond = conditioning.GeneralConditioner(conditioning.V3D_512_EMB_MODELS)
+    c, uc = conditioning.assemble_v3d_conditioning(cond, gold["clip_emb"], gold["latent"], 6.0, 127.0, 0.02, 18)
+    for k in ("vector", "crossattn", "concat"):
+        assert torch.equal(c[k], gold["c"][k]) and torch.equal(uc[k], gold["uc"][k]), k
+    assert c["vector"].shape == (18, 768) and uc["crossattn"].abs().sum() == 0 and uc["concat"].abs().sum() == 0
+    assert [e.ucg_rate for e in cond.embedders] == [0.2, 0.0, 0.0, 0.2, 0.0]   # restored after the call
+
+
 def test_drop_in_targets_resolve():
     from v3d_b200.sampling import get_obj_from_str
 
@@ -215,6 +235,9 @@ def test_drop_in_targets_resolve():
                        "sgm.modules.diffusionmodules.wrappers.OpenAIWrapper",
                        "sgm.modules.autoencoding.temporal_ae.VideoDecoder",
                        "sgm.modules.diffusionmodules.model.Encoder",
+                       "sgm.modules.encoders.modules.GeneralConditioner",
+                       "sgm.modules.encoders.modules.ConcatTimestepEmbedderND",
+                       "sgm.modules.encoders.modules.IdentityEncoder",
                        "sgm.modules.autoencoding.regularizers.DiagonalGaussianRegularizer",
                        "sgm.models.autoencoder.AutoencodingEngine",
                        "sgm.models.video_diffusion.DiffusionEngine"]:

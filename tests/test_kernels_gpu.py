@@ -419,3 +419,18 @@ def test_gemm_cta_pair_path_subprocess():
                           "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
+
+@_unvalidated
+def test_concat_timestep_embedder_device():
+    """Native ConcatTimestepEmbedderND vs the reference's vector conditioning (golden, fp32)."""
+    from pathlib import Path
+
+    from v3d_b200 import conditioning
+
+    gold = torch.load(Path(__file__).resolve().parent / "golden" / "conditioning.pt")
+    cond = conditioning.GeneralConditioner(conditioning.V3D_512_EMB_MODELS).to(DEV)
+    c, uc = conditioning.assemble_v3d_conditioning(cond, gold["clip_emb"].to(DEV), gold["latent"].to(DEV), 6.0, 127.0,
+                                                   0.02, 18)
+    assert torch.allclose(c["vector"].cpu(), gold["c"]["vector"], atol=2e-5)
+    assert torch.equal(c["crossattn"].cpu(), gold["c"]["crossattn"]) and torch.equal(uc["concat"].cpu(), gold["uc"]["concat"])
+
