@@ -125,7 +125,8 @@ class CpuReference:
 
     # (UNet latents, decoder latents, cost of one sample in units of the calibration forward); V3D_512 itself is 64
     LADDER = (((16, 32), (8, 16), 20.0), ((8, 16), (4, 8), 5.5))
-    BUDGET_S = 240.0     # all samples of a run (warm-up + timed) should fit in about this much CPU time
+    # all samples of a run (warm-up + timed) should fit in about this much CPU time (V3D_CPU_BUDGET_S overrides)
+    BUDGET_S = float(os.environ.get("V3D_CPU_BUDGET_S", "240"))
 
     def __init__(self, T: int, S: int, latent: int, n_samples: int = 1):
         import torch

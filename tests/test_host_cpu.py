@@ -255,3 +255,28 @@ def test_engine_builds_from_config_small():
     assert any(k.startswith("model.diffusion_model.input_blocks.0.0.weight") for k in keys)
     assert any(k.startswith("first_stage_model.decoder.conv_in.weight") for k in keys)
     assert eng.sampler.num_steps == 3 and eng.sampler.guider.num_frames == 4
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm) on the smallest sample ladder: one JSON line with the
+    contract's keys, the calibrated thread count and the raw two-size measurements."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, V3D_CPU_BUDGET_S="1")
+    res = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "view-frames/sec" and line["value"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert set(cb["last_sample_raw_s"]) == {"unet_s", "decode_s"} and cb["thread_calibration_s"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
