@@ -81,6 +81,12 @@ typedef struct v3d_gemm_args {
    * transposed (D[col][row] = acc + bias[row]), optionally accumulated into; columns >= valid_cols are dropped */
   int32_t out_transposed, valid_cols, accumulate;
   float s0, s1, s2;
+  /* halo'd A operand (linear / temporal modes; both 0 = none): every batch item of A holds a_rows >= a_row0 +
+   * rows_per_batch rows and output row r reads A row a_row0 + r (+ the tap shifts); rows outside [0, a_rows) read as
+   * zero.  Frame-sharded temporal convs pass a buffer with one halo frame on each side (a_row0 = tap_shift,
+   * a_rows = rows_per_batch + 2 * tap_shift): the neighbours' boundary frames of video_model.py:42-55 /
+   * temporal_ae.py:94-99 when the T view-frames are split across GPUs. */
+  int32_t a_rows, a_row0;
 } v3d_gemm_args;
 
 int v3d_gemm_bf16(const v3d_gemm_args* args, void* stream);
@@ -136,6 +142,13 @@ int v3d_attention_spatial_mma(const void* q, const void* k, const void* v, void*
  * frame-major token matrix in place: row(b,t,s) = (b*T + t)*S + s, T <= 32. */
 int v3d_attention_temporal(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
                            int32_t nb, int32_t T, int32_t S, int32_t nheads, float scale, void* stream);
+/* frame-sharded form (the "temporal-attention KV all-gather" of BASELINE.json): q / o hold this rank's
+ * Tq frames (row(b,t,s) = (b*Tq + t)*S + s); k / v point into the all-gathered K|V buffer (row stride ld_kv) where key
+ * frame f of CFG half b, pixel s is row kv_row[f] + b*kv_bstride[f] + s (host int32[Tk] arrays, rank-major layout).
+ * Tq <= Tk <= 32. */
+int v3d_attention_temporal_kv(const void* q, const void* k, const void* v, void* o, int64_t ld_q, int64_t ld_kv,
+                              int64_t ld_o, int32_t nb, int32_t Tq, int32_t Tk, int32_t S, int32_t nheads,
+                              const int32_t* kv_row, const int32_t* kv_bstride, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data movement / small matrices (elementwise.cu)

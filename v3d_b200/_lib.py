@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("block_n", C.c_int32),
         ("out_transposed", C.c_int32), ("valid_cols", C.c_int32), ("accumulate", C.c_int32),
         ("s0", C.c_float), ("s1", C.c_float), ("s2", C.c_float),
+        ("a_rows", C.c_int32), ("a_row0", C.c_int32),
     ]
 
 
@@ -56,6 +57,8 @@ SIGNATURES = {
     "v3d_attention_spatial": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "v3d_attention_spatial_mma": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "v3d_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "v3d_attention_temporal_kv": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), _f32, _vp]),
     # elementwise.cu
     "v3d_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "v3d_copy_channels": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),

@@ -6,6 +6,8 @@
 //   temporal: sequences of T <= 32 view-frames per (pixel, head); one warp per sequence, whole
 //             problem on chip, no online softmax. Reads q/k/v with the frame stride directly from the
 //             frame-major token matrix, so "(b t) s c -> (b s) t c" is never materialised.
+#include <cstring>
+
 #include "common.cuh"
 #include "host_util.cuh"
 #include "v3d_b200.h"
@@ -247,10 +249,21 @@ constexpr int kTaTile = 32 * 128;  // one [32 rows][64] bf16 tile, 128-byte rows
 //   O (32x64)                  = P V      : 2 m-tiles x 8 n-tiles x 2 k-steps
 // Q/K/V rows are gathered with the frame stride S*ld straight from the frame-major token matrix (cp.async,
 // 16-byte chunks), O is staged through the Q tile and written back as 16-byte chunks.
+//
+// SPLIT (frame-sharded views): the T query frames are this rank's block of the video while keys and
+// values come from all kv.tk frames of the K|V all-gather buffer, whose rows are rank-major: row of key frame f,
+// CFG half b, pixel s is kv.row[f] + b * kv.bstride[f] + s (row stride ldkv).  Keys >= kv.tk are masked.
+struct TaKV {
+  int tk;
+  int row[kMaxT];
+  int bstride[kMaxT];
+};
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTaWarps * 32)
 attn_temporal_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf16* __restrict__ V,
                      bf16* __restrict__ O, long long ld, long long ldo, int T, int S, int nheads,
-                     float scale_log2e) {
+                     float scale_log2e, long long ldkv, const __grid_constant__ TaKV kv) {
   extern __shared__ __align__(128) uint8_t ta_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -259,24 +272,51 @@ attn_temporal_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, con
   uint8_t* sk = sq + kTaTile;
   uint8_t* sv = sk + kTaTile;
   const long long row_base = (static_cast<long long>(b) * T) * S + s;
+  const int TK = SPLIT ? kv.tk : T;  // key / value frames
 
   // rows >= T of K and V are never loaded: zero them once (P is 0 there, but 0 * garbage must stay 0)
-  for (int i = lane; i < (32 - T) * 8; i += 32) {
-    const int r = T + (i >> 3), c = i & 7;
-    *reinterpret_cast<uint4*>(sk + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(sv + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(sq + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+  if (SPLIT) {
+    for (int i = lane; i < (32 - TK) * 8; i += 32) {
+      const int r = TK + (i >> 3), c = i & 7;
+      *reinterpret_cast<uint4*>(sk + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sv + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = lane; i < (32 - T) * 8; i += 32) {
+      const int r = T + (i >> 3), c = i & 7;
+      *reinterpret_cast<uint4*>(sq + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+    for (int i = lane; i < (32 - T) * 8; i += 32) {
+      const int r = T + (i >> 3), c = i & 7;
+      *reinterpret_cast<uint4*>(sk + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sv + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sq + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+    }
   }
 
   for (int head = warp; head < nheads; head += kTaWarps) {
     const long long col = static_cast<long long>(head) * HD;
     __syncwarp();
-    for (int i = lane; i < T * 8; i += 32) {
-      const int r = i >> 3, c = i & 7;
-      const long long off = (row_base + static_cast<long long>(r) * S) * ld + col + c * 8;
-      cp_async16(sq + tile_off(r, c), Q + off, true);
-      cp_async16(sk + tile_off(r, c), K + off, true);
-      cp_async16(sv + tile_off(r, c), V + off, true);
+    if (SPLIT) {
+      for (int i = lane; i < T * 8; i += 32) {
+        const int r = i >> 3, c = i & 7;
+        cp_async16(sq + tile_off(r, c), Q + (row_base + static_cast<long long>(r) * S) * ld + col + c * 8, true);
+      }
+      for (int i = lane; i < TK * 8; i += 32) {
+        const int r = i >> 3, c = i & 7;
+        const long long off =
+            (static_cast<long long>(kv.row[r]) + static_cast<long long>(b) * kv.bstride[r] + s) * ldkv + col + c * 8;
+        cp_async16(sk + tile_off(r, c), K + off, true);
+        cp_async16(sv + tile_off(r, c), V + off, true);
+      }
+    } else {
+      for (int i = lane; i < T * 8; i += 32) {
+        const int r = i >> 3, c = i & 7;
+        const long long off = (row_base + static_cast<long long>(r) * S) * ld + col + c * 8;
+        cp_async16(sq + tile_off(r, c), Q + off, true);
+        cp_async16(sk + tile_off(r, c), K + off, true);
+        cp_async16(sv + tile_off(r, c), V + off, true);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -319,8 +359,8 @@ attn_temporal_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int key = j * 8 + 2 * t;
-        if (key >= T) { sc[mt][j][0] = -INFINITY; sc[mt][j][2] = -INFINITY; }
-        if (key + 1 >= T) { sc[mt][j][1] = -INFINITY; sc[mt][j][3] = -INFINITY; }
+        if (key >= TK) { sc[mt][j][0] = -INFINITY; sc[mt][j][2] = -INFINITY; }
+        if (key + 1 >= TK) { sc[mt][j][1] = -INFINITY; sc[mt][j][3] = -INFINITY; }
         mx0 = fmaxf(mx0, fmaxf(sc[mt][j][0], sc[mt][j][1]));
         mx1 = fmaxf(mx1, fmaxf(sc[mt][j][2], sc[mt][j][3]));
       }
@@ -455,10 +495,48 @@ int v3d_attention_temporal(const void* q, const void* k, const void* v, void* o,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int smem = kTaWarps * 3 * kTaTile;
   dim3 grid(S, nb);
-  attn_temporal_kernel<<<grid, kTaWarps * 32, smem, st>>>(
+  TaKV none;
+  memset(&none, 0, sizeof(none));
+  none.tk = T;
+  attn_temporal_kernel<false><<<grid, kTaWarps * 32, smem, st>>>(
       static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
-      static_cast<bf16*>(o), ld_qkv, ld_o, T, S, nheads, scale * 1.44269504088896340736f);
+      static_cast<bf16*>(o), ld_qkv, ld_o, T, S, nheads, scale * 1.44269504088896340736f, ld_qkv, none);
   V3D_CHECK_LAUNCH("attn_temporal_kernel");
+  return V3D_OK;
+}
+
+/* Frame-sharded temporal self-attention (BASELINE.json "temporal-attention KV all-gather"): this
+ * rank holds Tq of the video's Tk view-frames.  q / o are the local frame-major token matrices (row(b,t,s) =
+ * (b*Tq + t)*S + s); k / v point into the all-gathered K|V buffer (row stride ld_kv) whose rows are rank-major, so
+ * key frame f of CFG half b, pixel s sits at row kv_row[f] + b * kv_bstride[f] + s (host int32 arrays of Tk entries).
+ * Same arithmetic as v3d_attention_temporal: softmax(q k^T scale) v over the Tk keys (attention.py:337-341 inside
+ * video_attention.py:114-125). */
+int v3d_attention_temporal_kv(const void* q, const void* k, const void* v, void* o, int64_t ld_q, int64_t ld_kv,
+                              int64_t ld_o, int32_t nb, int32_t Tq, int32_t Tk, int32_t S, int32_t nheads,
+                              const int32_t* kv_row, const int32_t* kv_bstride, float scale, void* stream) {
+  if (!q || !k || !v || !o || !kv_row || !kv_bstride || ld_q % 8 != 0 || ld_kv % 8 != 0 || ld_o % 8 != 0 ||
+      Tq <= 0 || Tq > Tk || Tk > kMaxT || nheads <= 0 || nb <= 0 || nb > 65535 || S <= 0) {
+    set_error("v3d_attention_temporal_kv: bad args (Tq=%d Tk=%d, need 0 < Tq <= Tk <= %d)", Tq, Tk, kMaxT);
+    return V3D_ERR_BAD_ARG;
+  }
+  TaKV kv;
+  memset(&kv, 0, sizeof(kv));
+  kv.tk = Tk;
+  for (int f = 0; f < Tk; ++f) {
+    if (kv_row[f] < 0 || kv_bstride[f] < 0) {
+      set_error("v3d_attention_temporal_kv: negative row offset for key frame %d", f);
+      return V3D_ERR_BAD_ARG;
+    }
+    kv.row[f] = kv_row[f];
+    kv.bstride[f] = kv_bstride[f];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int smem = kTaWarps * 3 * kTaTile;
+  dim3 grid(S, nb);
+  attn_temporal_kernel<true><<<grid, kTaWarps * 32, smem, st>>>(
+      static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
+      static_cast<bf16*>(o), ld_q, ld_o, Tq, S, nheads, scale * 1.44269504088896340736f, ld_kv, kv);
+  V3D_CHECK_LAUNCH("attn_temporal_kernel<split>");
   return V3D_OK;
 }
 

@@ -31,6 +31,7 @@ struct GemmEpi {
   long long ldd, ldr1, ldr2, ldfb;
   int batch, rows_per_batch, tiles_per_batch;
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
+  int tap0;  // A row coordinate of tap 0 relative to the output row: a_row0 - (ntaps / 2) * tap_shift
   int rows_per_frame, act, out_fp32;
   int b_batched;
   int fb_uniform;  // every 32-row warp slice of a tile lies in one frame: per-frame bias folds into the bias registers
@@ -214,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const int ky = tap / 3, kx = tap - ky * 3;
               tma_load_4d_2cta(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
             } else {
-              tma_load_3d_2cta(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift, c2);
+              tma_load_3d_2cta(sa, &mapA, &full_bar[stage], kc, c1 + tap * p.tap_shift + p.tap0, c2);
             }
             // this CTA's half of the B tile: rows [rank * BN/2, (rank + 1) * BN/2) of the N tile
             tma_load_3d_2cta(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN + cta_rank * (BN / 2), bz);
@@ -223,8 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const int ky = tap / 3, kx = tap - ky * 3;
               tma_load_4d(sa, &mapA, &full_bar[stage], kc, c1 + kx - 1, c2 + ky - 1, c3);
             } else {
-              tma_load_3d(sa, &mapA, &full_bar[stage], kc, c1 + (tap - (p.ntaps >> 1)) * p.tap_shift,
-                          c2);
+              tma_load_3d(sa, &mapA, &full_bar[stage], kc, c1 + tap * p.tap_shift + p.tap0, c2);
             }
             tma_load_3d(sb, &mapB, &full_bar[stage], kb * BK, n_tile * BN, bz);
           }
@@ -868,6 +868,7 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   e.kpt = a->K / BK;
   e.ntaps = ntaps;
   e.tap_shift = a->tap_shift;
+  e.tap0 = a->a_row0 - (ntaps >> 1) * a->tap_shift;
   e.rows_per_frame = a->rows_per_frame > 0 ? a->rows_per_frame : 1;
   e.act = a->act;
   e.out_fp32 = a->out_fp32;
@@ -949,12 +950,21 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     e.rows_per_batch = a->rows_per_batch;
     e.tiles_per_batch = (a->rows_per_batch + BM - 1) / BM;
     e.num_m_tiles = e.batch * e.tiles_per_batch;
-    const uint64_t abs_ = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->rows_per_batch * a->lda;
+    const uint64_t abs_ = a->batch > 1 ? (uint64_t)a->a_batch_stride
+                                       : (uint64_t)(a->a_rows > 0 ? a->a_rows : a->rows_per_batch) * a->lda;
     if (abs_ % 8 != 0) {
       set_error("v3d_gemm_bf16: a_batch_stride must be a multiple of 8");
       return V3D_ERR_BAD_ARG;
     }
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows_per_batch, (uint64_t)a->batch};
+    // halo'd operand (frame-sharded temporal convs): the tensor map spans a_rows >= rows_per_batch rows per batch
+    // item and output row r reads A rows a_row0 + r (+ tap shifts); rows outside [0, a_rows) are zero-filled
+    if (a->a_rows < 0 || a->a_row0 < 0 || (a->a_rows > 0 && a->a_rows < a->a_row0 + a->rows_per_batch)) {
+      set_error("v3d_gemm_bf16: bad halo geometry a_rows=%d a_row0=%d rows_per_batch=%d", a->a_rows, a->a_row0,
+                a->rows_per_batch);
+      return V3D_ERR_BAD_ARG;
+    }
+    const uint64_t a_rows = a->a_rows > 0 ? (uint64_t)a->a_rows : (uint64_t)a->rows_per_batch + (uint64_t)a->a_row0;
+    const uint64_t dims[3] = {(uint64_t)a->K, a_rows, (uint64_t)a->batch};
     const uint64_t str[2] = {(uint64_t)a->lda * 2, abs_ * 2};
     const uint32_t box[3] = {BK, BM, 1};
     rc = make_tmap_bf16(&ma, a->A, 3, dims, str, box);

@@ -229,15 +229,16 @@ class VideoDecoder(KernelModule):
         a = self._gn(P, name + ".norm2", h1, hw, B, co, 1e-6, True)
         skip = x if ci == co else self._linear(P, name + ".nin_shortcut", x, rows)
         xs = self._conv3x3(P, name + ".conv2", a, B, h, w, co, r1=skip, s1=1.0, out=h1)
+        # (frame-sharded: T is this rank's block; the 3-D norms all-reduce their statistics, the convs read halos)
         ts = name + ".time_stack"
-        a = self._gn(P, ts + ".in_layers.0", xs, T * hw, nb, co, 1e-5, True)
+        norm = self._gn_halo if self.view_shard is not None else None
+        a = (norm(P, ts + ".in_layers.0", xs, hw, T, nb, co, 1e-5, True) if norm else
+             self._gn(P, ts + ".in_layers.0", xs, T * hw, nb, co, 1e-5, True))
         h2 = torch.empty(rows, co, device=x.device, dtype=torch.bfloat16)
-        ops.gemm(a, P[ts + ".in_layers.2.weight"], h2, K=co, N=co, rows_per_batch=T * hw, batch=nb,
-                 a_batch_stride=T * hw * co, bias=P[ts + ".in_layers.2.bias"], ntaps=3, tap_shift=hw)
-        a = self._gn(P, ts + ".out_layers.0", h2, T * hw, nb, co, 1e-5, True)
-        ops.gemm(a, P[ts + ".out_layers.3.weight"], h2, K=co, N=co, rows_per_batch=T * hw, batch=nb,
-                 a_batch_stride=T * hw * co, bias=P[ts + ".out_layers.3.bias"], ntaps=3, tap_shift=hw,
-                 r1=xs, s1=1.0, s0=P[name + ".alpha"])
+        self._tconv(P, ts + ".in_layers.2", a, h2, hw, T, nb, co)
+        a = (norm(P, ts + ".out_layers.0", h2, hw, T, nb, co, 1e-5, True) if norm else
+             self._gn(P, ts + ".out_layers.0", h2, T * hw, nb, co, 1e-5, True))
+        self._tconv(P, ts + ".out_layers.3", a, h2, hw, T, nb, co, r1=xs, s1=1.0, s0=P[name + ".alpha"])
         return h2
 
     def _attn(self, P, key, c, x, B, h, w):
@@ -272,6 +273,11 @@ class VideoDecoder(KernelModule):
         T = int(timesteps) if timesteps else B
         assert B % T == 0 and zc == self.z_channels
         nb = B // T
+        vs = self.view_shard
+        if vs is not None:
+            # frame-sharded decode: z holds this rank's block of ONE video decoded as a whole (the reference with
+            # en_and_decode_n_samples_a_time = T, video_diffusion.py:182-210)
+            assert nb == 1 and T == vs.tl, f"view-sharded decode expects this rank's {vs.tl} frames, got {B} / T={T}"
         P = self.packed()
         dev = z.device
         n_norms = 4 * sum(1 for n, _, _ in self._blocks() if not n.startswith("@")) + 2
@@ -297,9 +303,22 @@ class VideoDecoder(KernelModule):
                     cur = self._video_res_block(P, name, ci, co, cur, B, T, nb, h, w)
                     ch = co
             a = self._gn(P, "norm_out", cur, h * w, B, ch, 1e-6, True)
-            o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
-            out = torch.empty(B, self.out_ch, h, w, device=dev, dtype=torch.float32)
-            ops.time_mix_conv(o, o.shape[1], P["time_mix.weight"], P["time_mix.bias"], out, nb, T, h * w, self.out_ch)
+            if vs is None:
+                o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
+                out = torch.empty(B, self.out_ch, h, w, device=dev, dtype=torch.float32)
+                ops.time_mix_conv(o, o.shape[1], P["time_mix.weight"], P["time_mix.bias"], out, nb, T, h * w,
+                                  self.out_ch)
+            else:
+                # AE3DConv's time_mix_conv (temporal_ae.py:101-107) is one more (3,1,1) conv: conv_out lands in the
+                # interior of a halo'd fp32 buffer, the mix runs over T + 2 frames and the two halo frames are dropped
+                cop = P["conv_out.weight"].shape[0]
+                pad = torch.empty(1, T + 2, h * w, cop, device=dev, dtype=torch.float32)
+                self._conv3x3(P, "conv_out", a, B, h, w, ch, out=pad[0, 1:T + 1].view(B * h * w, cop))
+                vs.exchange_halos(pad)
+                full = torch.empty(T + 2, self.out_ch, h, w, device=dev, dtype=torch.float32)
+                ops.time_mix_conv(pad.view(-1, cop), cop, P["time_mix.weight"], P["time_mix.bias"], full, 1, T + 2,
+                                  h * w, self.out_ch)
+                out = full[1:T + 1].contiguous()
             object.__setattr__(self, "_gn_pool", None)
             return out
 

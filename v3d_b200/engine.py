@@ -6,6 +6,7 @@ EMA, losses, loggers) are out of scope.
 """
 from __future__ import annotations
 
+import copy
 import math
 from typing import Dict, Optional
 
@@ -121,9 +122,14 @@ class DiffusionEngine(nn.Module):
 
     @torch.no_grad()
     def sample_views(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int,
-                     decoding_t: Optional[int] = None) -> torch.Tensor:
+                     decoding_t: Optional[int] = None, view_shard=None) -> torch.Tensor:
         """The hot path of sample_one (scripts/pub/V3D_512.py:269-285): sampler loop + first-stage decode.
-        randn [T,4,h,w] fp32 (scaled in place, as in the reference); returns [T,3,8h,8w] fp32."""
+        randn [T,4,h,w] fp32 (scaled in place, as in the reference); returns [T,3,8h,8w] fp32.
+
+        `view_shard` (v3d_b200.viewshard.ViewShard): every rank passes the SAME full-video randn / c / uc and gets
+        back the decoded frames of its own block [tl,3,8h,8w] (`view_shard.gather_frames` assembles the video)."""
+        if view_shard is not None:
+            return self._sample_views_sharded(randn, c, uc, num_frames, view_shard)
         extra = {"image_only_indicator": torch.zeros(2, num_frames, device=randn.device),
                  "num_video_frames": num_frames}
 
@@ -133,3 +139,28 @@ class DiffusionEngine(nn.Module):
         samples_z = self.sampler(denoiser, randn, cond=c, uc=uc)
         self.en_and_decode_n_samples_a_time = decoding_t or min(24, num_frames)
         return self.decode_first_stage(samples_z)
+
+    @torch.no_grad()
+    def _sample_views_sharded(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int, vs) -> torch.Tensor:
+        """One image, T view-frames split across the ranks of `vs`.  The sampler state, the CFG pair
+        and the Euler update of a frame stay on its rank; the UNet and the decoder exchange K|V, conv halos and 3-D
+        GroupNorm statistics through `vs`.  The video is decoded as one chunk (decoding_t = T)."""
+        assert vs.num_frames == num_frames and randn.shape[0] == num_frames
+        unet = self.model.diffusion_model
+        decoder = self.first_stage_model.decoder
+        x = randn[vs.frames].clone()
+        c_l, uc_l = vs.shard_cond(c), vs.shard_cond(uc)
+        extra = {"image_only_indicator": torch.zeros(2, vs.tl, device=randn.device),
+                 "num_video_frames": vs.tl, "time_context": vs.time_context(c, uc)}
+
+        def denoiser(inp, sigma, cond):
+            return self.denoiser(self.model, inp, sigma, cond, **extra)
+
+        sampler = copy.copy(self.sampler)
+        sampler.guider = vs.shard_guider(self.sampler.guider)
+        unet.view_shard = decoder.view_shard = vs
+        try:
+            z = sampler(denoiser, x, cond=c_l, uc=uc_l)
+            return self.first_stage_model.decode(1.0 / self.scale_factor * z, timesteps=vs.tl)
+        finally:
+            unet.view_shard = decoder.view_shard = None

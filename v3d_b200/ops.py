@@ -55,8 +55,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
          r1: Optional[torch.Tensor] = None, ldr1: int = 0, r2: Optional[torch.Tensor] = None, ldr2: int = 0,
          s0: float = 1.0, s1: float = 1.0, s2: float = 1.0, act: int = ACT_NONE, ntaps: int = 1,
          tap_shift: int = 0, conv: Optional[tuple] = None, block_n: int = 0, transposed: bool = False,
-         valid_cols: int = 0, accumulate: bool = False) -> torch.Tensor:
-    """General entry to v3d_gemm_bf16. `conv=(n, h, w)` selects the implicit 3x3 conv gather."""
+         valid_cols: int = 0, accumulate: bool = False, a_rows: int = 0, a_row0: int = 0) -> torch.Tensor:
+    """General entry to v3d_gemm_bf16. `conv=(n, h, w)` selects the implicit 3x3 conv gather; `a_rows` / `a_row0`
+    describe a halo'd A operand (frame-sharded temporal convs, see include/v3d_b200.h)."""
     _need(a, torch.bfloat16, "gemm A")
     _need(w, torch.bfloat16, "gemm B")
     g = GemmArgs()
@@ -89,6 +90,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
     g.valid_cols = valid_cols
     g.accumulate = 1 if accumulate else 0
     g.s0, g.s1, g.s2 = s0, s1, s2
+    g.a_rows, g.a_row0 = a_rows, a_row0
     _lib.check(_lib.load().v3d_gemm_bf16(C.byref(g), _stream()), "v3d_gemm_bf16")
     return out
 
@@ -182,6 +184,24 @@ def attention_temporal(qkv: torch.Tensor, out: torch.Tensor, nb: int, t: int, s:
     _lib.check(_lib.load().v3d_attention_temporal(base, base + c * es, base + 2 * c * es, out.data_ptr(),
                                                   qkv.shape[-1], out.shape[-1], nb, t, s, nheads, scale,
                                                   _stream()), "v3d_attention_temporal")
+    return out
+
+
+def attention_temporal_kv(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, nb: int, tq: int, s: int, nheads: int,
+                          kv_row, kv_bstride, scale: float) -> torch.Tensor:
+    """Frame-sharded temporal attention: q = the query columns of the local packed projection ([nb*tq*s, ld_q] view),
+    kv = the all-gathered [rows, 2C] K|V buffer, kv_row / kv_bstride = per key frame row offsets (python ints)."""
+    _need(q, torch.bfloat16, "attention q")
+    _need(kv, torch.bfloat16, "attention kv")
+    c = nheads * 64
+    tk = len(kv_row)
+    rows_t = (C.c_int32 * tk)(*kv_row)
+    bstr_t = (C.c_int32 * tk)(*kv_bstride)
+    base = kv.data_ptr()
+    _lib.check(_lib.load().v3d_attention_temporal_kv(q.data_ptr(), base, base + c * kv.element_size(), out.data_ptr(),
+                                                     q.stride(0), kv.stride(0), out.stride(0), nb, tq, tk, s, nheads,
+                                                     rows_t, bstr_t, scale, _stream()),
+               "v3d_attention_temporal_kv")
     return out
 
 

@@ -156,23 +156,55 @@ class KernelModule(nn.Module):
     def _new(rows: int, c: int, dev, dtype=torch.bfloat16) -> torch.Tensor:
         return torch.empty(rows, c, device=dev, dtype=dtype)
 
-    def _gn(self, P: dict, key: str, x: torch.Tensor, rows_per_sample: int, nsamples: int, c: int, eps: float,
-            silu: bool) -> torch.Tensor:
+    # frame-sharded execution (v3d_b200.viewshard.ViewShard) or None: set by the engine around a sharded call
+    view_shard = None
+
+    def _take_stats(self, nsamples: int, dev) -> Tuple[torch.Tensor, bool]:
         # statistics slices come out of one pool zeroed once per forward (one memset instead of one per norm)
         pool = getattr(self, "_gn_pool", None)
         need = nsamples * 64
         if pool is not None and pool[1] + need <= pool[0].numel():
             stats = pool[0][pool[1]:pool[1] + need].view(nsamples, 32, 2)
             pool[1] += need
-            pre_zeroed = True
-        else:
-            stats = torch.empty(nsamples, 32, 2, device=x.device, dtype=torch.float64)
-            pre_zeroed = False
+            return stats, True
+        return torch.empty(nsamples, 32, 2, device=dev, dtype=torch.float64), False
+
+    def _gn(self, P: dict, key: str, x: torch.Tensor, rows_per_sample: int, nsamples: int, c: int, eps: float,
+            silu: bool) -> torch.Tensor:
+        stats, pre_zeroed = self._take_stats(nsamples, x.device)
         y = torch.empty(x.shape[0], c, device=x.device, dtype=torch.bfloat16)
         ops.groupnorm_stats(x, stats, rows_per_sample, nsamples, c, pre_zeroed=pre_zeroed)
         ops.groupnorm_apply(x, y, stats, P[key + ".weight"], P[key + ".bias"], rows_per_sample, nsamples, c, eps,
                             silu)
         return y
+
+    def _gn_halo(self, P: dict, key: str, x: torch.Tensor, hw: int, tl: int, nb: int, c: int, eps: float,
+                 silu: bool) -> torch.Tensor:
+        """3-D GroupNorm (+SiLU) of a frame-sharded video: local (sum, sumsq) -> all-reduce -> apply, written into
+        the interior of a [nb, tl + 2, hw, c] buffer whose first / last frame then receive the neighbours' boundary
+        frames (zeros at the ends of the video): the operand of the following (3,1,1) convolution."""
+        vs = self.view_shard
+        stats, pre_zeroed = self._take_stats(nb, x.device)
+        ops.groupnorm_stats(x, stats, tl * hw, nb, c, pre_zeroed=pre_zeroed)
+        vs.allreduce_stats_(stats)
+        pad = torch.empty(nb, tl + 2, hw, c, device=x.device, dtype=torch.bfloat16)
+        for b in range(nb):
+            ops.groupnorm_apply(x[b * tl * hw:(b + 1) * tl * hw], pad[b, 1:tl + 1], stats[b:b + 1],
+                                P[key + ".weight"], P[key + ".bias"], tl * hw, 1, c, eps, silu)
+        vs.exchange_halos(pad)
+        return pad
+
+    def _tconv(self, P: dict, key: str, a: torch.Tensor, out: torch.Tensor, hw: int, T: int, nb: int, c: int,
+               **epi) -> torch.Tensor:
+        """Conv3d k=(3,1,1) pad (1,0,0) on the frame-major layout as a 3-tap GEMM.  `a` is either the dense
+        [nb*T*hw, c] activation (zero padding at both ends of every video) or, frame-sharded, the halo'd
+        [nb, T + 2, hw, c] buffer of `_gn_halo`."""
+        halo = a.dim() == 4
+        frames = T + 2 if halo else T
+        ops.gemm(a.view(-1, c) if halo else a, P[key + ".weight"], out, K=c, N=c, rows_per_batch=T * hw, batch=nb,
+                 a_batch_stride=frames * hw * c, bias=P[key + ".bias"], ntaps=3, tap_shift=hw,
+                 a_rows=frames * hw if halo else 0, a_row0=hw if halo else 0, **epi)
+        return out
 
     def _conv3x3(self, P: dict, key: str, x: torch.Tensor, n: int, h: int, w: int, cin: int, *, stride: int = 1,
                  out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, **epi) -> torch.Tensor:
@@ -626,15 +658,28 @@ class VideoUNet(KernelModule):
         self._check_indicator(image_only_indicator, nb, T)
         P = self.packed()
         dev = x.device
-        args = (x.float().contiguous(), timesteps.float().contiguous(),
-                context.float().reshape(B, -1).contiguous(), y.float().contiguous())
+        ctx2d = context.float().reshape(B, -1)
+        vs = self.view_shard
+        graphs = self.cuda_graphs
+        if vs is not None:
+            # frame-sharded call: x / context / y hold this rank's T = vs.tl frames of each video; the temporal
+            # cross-attention context (frame 0 of each video, video_attention.py:250) may live on another rank and
+            # arrives through `time_context` [nb, 1, ctx]; its rows are appended to the context matrix
+            assert T == vs.tl, f"view-sharded forward expects this rank's {vs.tl} frames, got num_video_frames={T}"
+            assert time_context is not None and time_context.shape[0] == nb and time_context.ndim == 3, \
+                "view-sharded forward needs time_context = context of frame 0 of each video, [nb, 1, ctx]"
+            ctx2d = torch.cat([ctx2d, time_context.float().reshape(nb, -1).to(dev)], dim=0)
+            # collectives inside a captured graph are opt-in until validated on hardware
+            graphs = graphs and os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1" and not vs._via_host(x)
+        args = (x.float().contiguous(), timesteps.float().contiguous(), ctx2d.contiguous(), y.float().contiguous())
         with torch.no_grad():
-            if self.cuda_graphs and self.debug_taps is None and not torch.cuda.is_current_stream_capturing():
+            if graphs and self.debug_taps is None and not torch.cuda.is_current_stream_capturing():
                 return self._run_graphed(P, args, B, T, nb, H, W, dev)
             return self._run(P, *args, B, T, nb, H, W, dev)
 
     def _run_graphed(self, P, args, B, T, nb, H, W, dev):
-        key = (B, T, H, W, dev.index)
+        vs = self.view_shard
+        key = (B, T, H, W, dev.index) if vs is None else (B, T, H, W, dev.index, vs.num_frames, vs.rank, vs.world)
         entry = self._graphs.get(key)
         if entry is None:
             # first call with this shape runs eagerly: warms kernel attributes and the positional-embedding cache
@@ -673,9 +718,10 @@ class VideoUNet(KernelModule):
         emb_all = torch.empty(B, P["emb_total"], device=dev)
         ops.small_linear(emb, P["emb_all.weight"], P["emb_all.bias"], emb_all, act_in=ops.ACT_SILU)
         # single-token cross-attention: v = to_v(ctx) for every layer in one launch, then to_out per layer
-        v_all = torch.empty(B, P["cv_total"], device=dev)
+        nctx = ctx2d.shape[0]  # B, plus one time-context row per video when frame-sharded
+        v_all = torch.empty(nctx, P["cv_total"], device=dev)
         ops.small_linear(ctx2d, P["cv_all.weight"], None, v_all)
-        cross = torch.empty(B, P["cv_total"], device=dev)
+        cross = torch.empty(nctx, P["cv_total"], device=dev)
         for base, (o, c) in P["cv_off"].items():
             ops.small_linear(v_all[:, o:o + c], P[base + ".attn2.to_out.0.weight"], P[base + ".attn2.to_out.0.bias"],
                              cross[:, o:o + c])
@@ -684,10 +730,11 @@ class VideoUNet(KernelModule):
     def _pos_emb(self, P, name: str, c: int, B: int, T: int, dev) -> torch.Tensor:
         """time_pos_embed(timestep_embedding(arange(T))) (video_attention.py:266-276): input-independent, cached
         per (layer, B, T) until the weights are re-packed."""
-        key = (name, B, T)
+        t0 = self.view_shard.t0 if self.view_shard is not None else 0  # frame ids are global (arange(T_video))
+        key = (name, B, T, t0)
         cache = P["pos_cache"]
         if key not in cache:
-            frames = torch.arange(T, device=dev, dtype=torch.float32).repeat(B // T)
+            frames = torch.arange(t0, t0 + T, device=dev, dtype=torch.float32).repeat(B // T)
             t_emb = torch.empty(B, c, device=dev)
             ops.timestep_embedding(frames, t_emb, c, float(self.max_ddpm_temb_period))
             h = torch.empty(B, 4 * c, device=dev)
@@ -713,18 +760,17 @@ class VideoUNet(KernelModule):
         skip = x if cin == cout else self._linear(P, nm + ".skip_connection", x, rows)
         xs = self._conv3x3(P, nm + ".out_layers.3", a, B, h, w, cout, r1=skip, s1=1.0, out=h1)
         # time_stack: GroupNorm over (C/32, T, H, W) per video, 3-tap temporal convs on the frame-major layout
+        # (frame-sharded: T is this rank's block; the norms all-reduce their statistics and the convs read halos)
         ts = nm + ".time_stack"
-        a = self._gn(P, ts + ".in_layers.0", xs, T * hw, nb, cout, 1e-5, True)
-        wt = P[ts + ".in_layers.2.weight"]
+        norm = self._gn_halo if self.view_shard is not None else None
+        a = (norm(P, ts + ".in_layers.0", xs, hw, T, nb, cout, 1e-5, True) if norm else
+             self._gn(P, ts + ".in_layers.0", xs, T * hw, nb, cout, 1e-5, True))
         h2 = torch.empty(rows, cout, device=x.device, dtype=torch.bfloat16)
-        ops.gemm(a, wt, h2, K=cout, N=cout, rows_per_batch=T * hw, batch=nb, a_batch_stride=T * hw * cout,
-                 bias=P[ts + ".in_layers.2.bias"], fbias=emb_all[:, o3:], ldfb=E, rows_per_frame=hw, ntaps=3,
-                 tap_shift=hw)
-        a = self._gn(P, ts + ".out_layers.0", h2, T * hw, nb, cout, 1e-5, True)
+        self._tconv(P, ts + ".in_layers.2", a, h2, hw, T, nb, cout, fbias=emb_all[:, o3:], ldfb=E, rows_per_frame=hw)
+        a = (norm(P, ts + ".out_layers.0", h2, hw, T, nb, cout, 1e-5, True) if norm else
+             self._gn(P, ts + ".out_layers.0", h2, T * hw, nb, cout, 1e-5, True))
         alpha = P[nm + ".alpha"]
-        ops.gemm(a, P[ts + ".out_layers.3.weight"], h2, K=cout, N=cout, rows_per_batch=T * hw, batch=nb,
-                 a_batch_stride=T * hw * cout, bias=P[ts + ".out_layers.3.bias"], ntaps=3, tap_shift=hw,
-                 r1=xs, s1=1.0, s0=1.0 - alpha)
+        self._tconv(P, ts + ".out_layers.3", a, h2, hw, T, nb, cout, r1=xs, s1=1.0, s0=1.0 - alpha)
         return h2
 
     def _attn_block(self, P, st: _Step, x, cross, B, T, nb, h, w):
@@ -764,10 +810,21 @@ class VideoUNet(KernelModule):
         self._linear(P, ts + ".ff_in.net.2", g, rows, out=xm, r1=xm, s1=1.0)
         a = ln(ts + ".norm1", xm)
         qkv = self._linear(P, ts + ".attn1.qkv", a, rows, out=qkv)
-        ops.attention_temporal(qkv, o, nb, T, hw, heads, scale)
-        # temporal cross-attention context = context[::T] (video_attention.py:250): row b*T of `cross`
+        vs = self.view_shard
+        if vs is None:
+            ops.attention_temporal(qkv, o, nb, T, hw, heads, scale)
+            # temporal cross-attention context = context[::T] (video_attention.py:250): row b*T of `cross`
+            tc_bias, tc_ld = cross[:, ot:], X * T
+        else:
+            # frame-sharded: all-gather the packed K|V rows of every rank's frames, attend in place through the
+            # per-frame row table; the time context (global frame 0 of each CFG half) is rows B.. of `cross`
+            send = torch.empty(nb * vs.tmax * hw, 2 * c, device=dev, dtype=torch.bfloat16)
+            ops.copy_channels(qkv[:, c:], 3 * c, send.data_ptr(), 2 * c, rows, 2 * c)
+            kv_row, kv_bstride = vs.kv_table(nb, hw)
+            ops.attention_temporal_kv(qkv, vs.gather_rows(send), o, nb, T, hw, heads, kv_row, kv_bstride, scale)
+            tc_bias, tc_ld = cross[B:, ot:], X
         self._linear(P, ts + ".attn1.to_out.0", o, rows, out=xm, r1=xm, s1=1.0,
-                     fbias=cross[:, ot:], ldfb=X * T, rows_per_frame=T * hw)
+                     fbias=tc_bias, ldfb=tc_ld, rows_per_frame=T * hw)
         a = ln(ts + ".norm3", xm)
         g = self._linear(P, ts + ".ff.net.0.proj", a, rows, out=g, act=ops.ACT_GEGLU)
         alpha = P[nm + ".alpha"]

@@ -1,0 +1,215 @@
+"""View-sharding ONE image across GPUs: the T view-frames of a video are split into contiguous blocks, one block
+per rank (BASELINE.json configs[2-3]).
+
+Everything that is per-frame or per-token stays rank-local (all spatial layers, the temporal feed-forwards and
+projections: ~93 % of the UNet's FLOPs).  Three things couple the frames and each gets one exchange:
+
+  * temporal self-attention (video_attention.py:114-125 around attention.py:337-341): every query frame attends to
+    the keys/values of all T frames -> all-gather of the packed K|V rows (`gather_rows`), consumed in place by
+    v3d_attention_temporal_kv through a per-frame row table (`kv_table`), so uneven blocks need no compaction;
+  * the (3,1,1) temporal convolutions (video_model.py:42-55, temporal_ae.py:94-99): one halo frame from each
+    neighbour (`exchange_halos`); the video's first / last frame keep the reference's ZERO padding;
+  * the 3-D GroupNorms of the time_stack ResBlocks (openaimodel.py:267-271 with dims=3): (sum, sum of squares)
+    all-reduce of the fp64 statistics (`allreduce_stats_`).
+
+The CFG pair [uc; c] of a frame lives on the same rank, so the guidance combine and the Euler update are local.
+This module is host logic over torch.distributed only (NCCL on GPUs; gloo in the CPU tests, and - staged through
+host memory - for 2 processes sharing one GPU in tests/test_viewshard_gpu.py); it launches no kernels of its own.
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition_frames(num_frames: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous (first frame, count) per rank; the first `num_frames % world` ranks take one extra frame.
+    T=18: 2 ranks 9/9, 4 ranks 5/5/4/4, 8 ranks 3/3/2/2/2/2/2/2."""
+    if world <= 0 or num_frames < world:
+        raise ValueError(f"cannot split {num_frames} frames over {world} ranks (every rank needs a frame)")
+    base, rem = divmod(num_frames, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((start, n))
+        start += n
+    return out
+
+
+@dataclass
+class ViewShard:
+    """This rank's block of a T-frame video and the exchanges that stitch the blocks together."""
+
+    num_frames: int                      # T of the whole video
+    rank: int
+    world: int
+    group: Optional[object] = None       # torch.distributed process group (None = default group)
+    blocks: List[Tuple[int, int]] = field(default_factory=list)
+    exchanges: Dict[str, int] = field(default_factory=dict)  # per-kind call counters (bench / tests)
+
+    @classmethod
+    def create(cls, num_frames: int, group=None) -> "ViewShard":
+        if not dist.is_initialized():
+            raise RuntimeError("ViewShard.create needs an initialised torch.distributed process group")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        return cls(num_frames, rank, world, group, partition_frames(num_frames, world))
+
+    def __post_init__(self):
+        if not self.blocks:
+            self.blocks = partition_frames(self.num_frames, self.world)
+        self._staged: Optional[bool] = None
+
+    # ---- geometry -------------------------------------------------------------------------------
+    @property
+    def t0(self) -> int:
+        return self.blocks[self.rank][0]
+
+    @property
+    def tl(self) -> int:
+        return self.blocks[self.rank][1]
+
+    @property
+    def tmax(self) -> int:
+        return max(n for _, n in self.blocks)
+
+    @property
+    def frames(self) -> slice:
+        return slice(self.t0, self.t0 + self.tl)
+
+    def kv_table(self, nb: int, rows_per_frame: int) -> Tuple[List[int], List[int]]:
+        """Row offsets of every key frame in the buffer `gather_rows` returns for a [nb, tl, rows_per_frame] block
+        per rank: frame f of video b, pixel s sits at row[f] + b * bstride[f] + s."""
+        row, bstride = [], []
+        block_rows = nb * self.tmax * rows_per_frame      # every rank's slot is padded to the largest block
+        for r, (_, n) in enumerate(self.blocks):
+            for j in range(n):
+                row.append(r * block_rows + j * rows_per_frame)
+                bstride.append(n * rows_per_frame)
+        return row, bstride
+
+    # ---- transport ------------------------------------------------------------------------------
+    def _via_host(self, t: torch.Tensor) -> bool:
+        """gloo cannot move CUDA memory for every primitive: stage through the host (tests only; NCCL is direct)."""
+        if self._staged is None:
+            self._staged = dist.get_backend(self.group) == "gloo"
+        return self._staged and t.is_cuda
+
+    def _count(self, kind: str) -> None:
+        self.exchanges[kind] = self.exchanges.get(kind, 0) + 1
+
+    def _global_rank(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def allreduce_stats_(self, stats: torch.Tensor) -> torch.Tensor:
+        """stats: fp64 [nsamples, groups, 2] = local (sum, sumsq) of a 3-D GroupNorm.  After the call it holds the
+        GLOBAL sums rescaled by tl / T, so that the apply kernel - which divides by the LOCAL element count - yields
+        the global mean and variance."""
+        self._count("gn_allreduce")
+        if self.world > 1:
+            if self._via_host(stats):
+                h = stats.cpu()
+                dist.all_reduce(h, group=self.group)
+                stats.copy_(h)
+            else:
+                dist.all_reduce(stats, group=self.group)
+        stats.mul_(self.tl / self.num_frames)
+        return stats
+
+    def exchange_halos(self, pad: torch.Tensor) -> torch.Tensor:
+        """pad: [nb, tl + 2, ...] contiguous; frames 1..tl are this rank's, frame 0 / tl+1 receive the previous /
+        next rank's last / first frame.  The ends of the video get zeros (Conv3d padding (1,0,0))."""
+        self._count("halo")
+        nb, tl = pad.shape[0], self.tl
+        assert pad.shape[1] == tl + 2 and pad.is_contiguous()
+        prev_r, next_r = self.rank - 1, self.rank + 1
+        if prev_r < 0:
+            pad[:, 0].zero_()
+        if next_r >= self.world:
+            pad[:, tl + 1].zero_()
+        if self.world == 1:
+            return pad
+        staged = self._via_host(pad)
+        ops, landing = [], []
+        for b in range(nb):
+            for peer, send_idx, recv_idx, tag_s, tag_r in ((prev_r, 1, 0, 0, 1), (next_r, tl, tl + 1, 1, 0)):
+                if peer < 0 or peer >= self.world:
+                    continue
+                src, dst = pad[b, send_idx], pad[b, recv_idx]
+                if staged:
+                    src = src.cpu()
+                    host = torch.empty(dst.shape, dtype=dst.dtype)
+                    landing.append((dst, host))
+                    dst = host
+                g = self._global_rank(peer)
+                # a frame sent "towards lower ranks" (tag_s 0) is received by the peer as its right halo (tag_r 0)
+                ops.append(dist.P2POp(dist.isend, src, g, group=self.group, tag=2 * b + tag_s))
+                ops.append(dist.P2POp(dist.irecv, dst, g, group=self.group, tag=2 * b + tag_r))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for dst, host in landing:
+            dst.copy_(host)
+        return pad
+
+    def gather_rows(self, send: torch.Tensor) -> torch.Tensor:
+        """send: [nb * tmax * rows_per_frame, W], of which this rank filled its first nb * tl * rows_per_frame rows.
+        Returns [world * rows, W] with rank r's block at r * rows (see `kv_table`)."""
+        self._count("kv_allgather")
+        if self.world == 1:
+            return send
+        out = send.new_empty((self.world * send.shape[0],) + tuple(send.shape[1:]))
+        if self._via_host(send):
+            h = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(h, send.cpu(), group=self.group)
+            out.copy_(h)
+        else:
+            dist.all_gather_into_tensor(out, send.contiguous(), group=self.group)
+        return out
+
+    def gather_frames(self, local: torch.Tensor) -> torch.Tensor:
+        """[tl, ...] per rank -> [T, ...] on every rank in frame order (the final decoded-frame gather)."""
+        self._count("frame_gather")
+        if self.world == 1:
+            return local
+        pad = local.new_zeros((self.tmax,) + tuple(local.shape[1:]))
+        pad[: self.tl] = local
+        out = local.new_empty((self.world * self.tmax,) + tuple(local.shape[1:]))
+        if self._via_host(local):
+            h = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(h, pad.cpu(), group=self.group)
+            out.copy_(h)
+        else:
+            dist.all_gather_into_tensor(out, pad, group=self.group)
+        out = out.reshape(self.world, self.tmax, *local.shape[1:])
+        return torch.cat([out[r, :n] for r, (_, n) in enumerate(self.blocks)], dim=0)
+
+    # ---- sampler-side slicing -------------------------------------------------------------------
+    def shard_cond(self, cond: Dict) -> Dict:
+        """Per-frame conditioning tensors ([T, ...]: vector, crossattn, concat) -> this rank's frames; other entries
+        pass through (guiders.py:88-98 treats them as shared)."""
+        out = {}
+        for k, v in cond.items():
+            if torch.is_tensor(v) and v.ndim > 0 and v.shape[0] == self.num_frames:
+                out[k] = v[self.frames].contiguous()
+            else:
+                out[k] = v
+        return out
+
+    def time_context(self, c: Dict, uc: Dict) -> torch.Tensor:
+        """The temporal cross-attention context is `context[::T]` = frame 0 of each CFG half
+        (video_attention.py:250): [2, 1, ctx] in [uc; c] order, the same on every rank."""
+        return torch.cat([uc["crossattn"][:1], c["crossattn"][:1]], dim=0).contiguous()
+
+    def shard_guider(self, guider):
+        """Copy of a per-frame guider (guiders.py:60-146) restricted to this rank's frames."""
+        if getattr(guider, "num_frames", 1) != self.num_frames:
+            return guider  # VanillaCFG / IdentityGuider: one scale for every sample
+        g = copy.copy(guider)
+        g.num_frames = self.tl
+        g.scale = guider.scale[:, self.frames].clone()
+        if hasattr(g, "_scale_dev"):
+            g._scale_dev = None
+        return g
