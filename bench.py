@@ -269,7 +269,10 @@ def workload_config(args, where: str) -> dict:
                         f"{args.edm_steps} Euler-EDM steps (CFG, B={2 * args.frames}) + first-stage decode; one image per GPU",
             "frames": args.frames, "edm_steps": args.edm_steps, "latent": [4, args.latent, args.latent],
             "cfg_scale": [args.min_cfg, args.max_cfg], "sigma_max": 700.0, "decode_chunk": args.frames,
-            "parallelism": f"image-dp{args.gpus}" if where != "cpu" else "host-cpu",
+            "parallelism": ("host-cpu" if where == "cpu" else
+                            f"view-shard{args.gpus}: the {args.frames} frames of ONE image split over the ranks "
+                            "(K|V all-gather, conv halos, 3-D GN all-reduce)" if getattr(args, "shard", "images") == "views"
+                            else f"image-dp{args.gpus}"),
             "l2_policy": "working set per step (3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
             "weights": "random-init (seeded), zero-init modules re-randomised",
             "cuda_graph": os.environ.get("V3D_CUDA_GRAPH", "1") != "0"}
@@ -296,12 +299,20 @@ def run_native(args) -> None:
     cfg = engine.v3d_512_config(num_frames=T, num_steps=S, min_cfg=args.min_cfg, max_cfg=args.max_cfg)
     with torch.device("meta"):
         eng = engine.DiffusionEngine(**cfg)
-    eng.model.diffusion_model.init_random_(dev, seed=100 + rank)
-    eng.first_stage_model.decoder.init_random_(dev, seed=200 + rank)
+    # --shard views: ONE image, its T frames split over the ranks (strong scaling): every rank holds
+    # the same weights and the same full-video inputs and samples / decodes its own block of frames
+    view_shard = None
+    if args.shard == "views":
+        from v3d_b200.viewshard import ViewShard
+
+        view_shard = (ViewShard.create(T) if world > 1 else ViewShard(num_frames=T, rank=0, world=1))
+    wrank = 0 if view_shard is not None else rank
+    eng.model.diffusion_model.init_random_(dev, seed=100 + wrank)
+    eng.first_stage_model.decoder.init_random_(dev, seed=200 + wrank)
     eng.eval()
 
-    # synthetic inputs in pinned host memory (one image per rank)
-    g = torch.Generator().manual_seed(23 + rank)
+    # synthetic inputs in pinned host memory (one image per rank; the same image on every rank when view-sharded)
+    g = torch.Generator().manual_seed(23 + wrank)
     host = {
         "x": torch.randn(T, 4, L, L, generator=g).pin_memory(),
         "c.crossattn": torch.randn(1, 1, 1024, generator=g).repeat(T, 1, 1).pin_memory(),
@@ -323,8 +334,8 @@ def run_native(args) -> None:
 
     def hot_path(x, c, uc):
         """The public API call a user makes: sampler loop + decode, then the uint8 THWC wire format."""
-        img = eng.sample_views(x, c, uc, num_frames=T, decoding_t=T)       # [T,3,H,W] fp32
-        u8 = torch.empty(T, 8 * L, 8 * L, 3, device=dev, dtype=torch.uint8)
+        img = eng.sample_views(x, c, uc, num_frames=T, decoding_t=T, view_shard=view_shard)  # [T or tl,3,H,W] fp32
+        u8 = torch.empty(img.shape[0], 8 * L, 8 * L, 3, device=dev, dtype=torch.uint8)
         return ops.frames_nchw_to_u8(img.contiguous(), u8)
 
     x_res, c_res, uc_res = upload()
@@ -339,7 +350,12 @@ def run_native(args) -> None:
     def step_e2e():
         x, c, uc = upload()
         u8 = hot_path(x, c, uc)
-        if world > 1:
+        if view_shard is not None:
+            # the decoded-frame gather of the view-sharded path (uint8 THWC over NCCL), then D2H on rank 0
+            allf = view_shard.gather_frames(u8)
+            if rank == 0:
+                frames_host.copy_(allf, non_blocking=True)
+        elif world > 1:
             # the path's only exchange: final decoded-frame gather (uint8 THWC) over NCCL, then D2H on rank 0
             allf = parallel.gather_frames(u8.unsqueeze(0), counts)
             if rank == 0:
@@ -452,7 +468,7 @@ def run_native(args) -> None:
             traffic = None
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
-    n_img = world
+    n_img = 1 if view_shard is not None else world
     value = n_img * T * args.steps / secs
     e2e_value = n_img * T * args.steps / secs_e2e
     model_tf = work_tf(T, S, L)
@@ -460,10 +476,11 @@ def run_native(args) -> None:
     line = {
         "metric": "view-frames/sec", "value": value, "unit": "view-frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if view_shard is not None else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
         "config": workload_config(args, "gpu"),
         "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes * world,
-                "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": 1000.0 * secs_e2e / args.steps,
+                "d2h_bytes_per_step": d2h_bytes * n_img, "ms_per_step": 1000.0 * secs_e2e / args.steps,
                 "api": "DiffusionEngine.sample_views + frames_nchw_to_u8 (+ NCCL frame gather when N > 1)"},
         "gpu_launches": launches,
         "clocks": clk,
@@ -480,6 +497,9 @@ def run_native(args) -> None:
                       "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
         },
     }
+    if view_shard is not None:
+        line["view_shard"] = {"blocks": view_shard.blocks, "exchanges_total": dict(view_shard.exchanges),
+                              "cuda_graph": os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(T, S, L)
         tu, td = ref.sample()
@@ -505,6 +525,9 @@ def main():
     ap.add_argument("--min-cfg", type=float, default=3.5)
     ap.add_argument("--max-cfg", type=float, default=3.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", choices=["images", "views"], default="images",
+                    help="images (default): one image per GPU, weak scaling.  views: ONE image, its frames split "
+                         "across the GPUs (strong scaling; K|V all-gather, conv halos, 3-D GroupNorm all-reduce)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         print("warning: timing rules ask for >= 3 warm-up steps", file=sys.stderr)

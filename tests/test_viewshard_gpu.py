@@ -1,0 +1,193 @@
+"""Frame-sharded (view-sharded) CUDA path vs the unsharded CUDA path.
+
+Kernel level (one process): the halo'd-operand mode of the tap GEMM and the split-KV temporal attention must give the
+SAME BITS as the dense kernels on the frames they own (same K order, same tile arithmetic).
+Model level: two processes run `DiffusionEngine.sample_views(view_shard=...)` on an uneven 3/2 split of T=5 frames
+and compare with the unsharded engine - over gloo with both ranks on cuda:0 (exchanges staged through the host, so it
+runs on a one-GPU box) and over NCCL on two GPUs when the box has them.  The only arithmetic difference is the
+summation order of the fp64 GroupNorm statistics, so the tolerance is far below the bf16 parity tolerance:
+rel-L2 <= 5e-3 on the decoded frames after 2 EDM steps, <= 2e-3 on one UNet forward.
+"""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+# first hardware run pending (written after the round-1 GPU budget was spent): enabled with V3D_RUN_UNVALIDATED=1;
+# tests/test_zzz_first_run_gpu.py runs this file that way in a child process at the end of the GPU suite
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
+                                 reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")]
+
+ROOT = str(Path(__file__).resolve().parent.parent)
+DEV = "cuda"
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# kernel level
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw,c,T,blocks", [(64, 320, 5, [(0, 3), (3, 2)]), (256, 128, 6, [(0, 2), (2, 2), (4, 2)]),
+                                           (4, 64, 5, [(0, 3), (3, 2)]), (1024, 64, 4, [(0, 1), (1, 3)])])
+def test_tap_gemm_halo_mode_equals_dense(hw, c, T, blocks):
+    from v3d_b200 import ops
+
+    nb = 2
+    g = torch.Generator(device=DEV).manual_seed(hw + c)
+    a = torch.randn(nb, T, hw, c, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(c, 3 * c, device=DEV, generator=g) / (3 * c) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(c, device=DEV, generator=g)
+    r1 = torch.randn(nb, T, hw, c, device=DEV, generator=g).to(torch.bfloat16)
+    dense = torch.empty(nb * T * hw, c, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a.view(-1, c), w, dense, K=c, N=c, rows_per_batch=T * hw, batch=nb, a_batch_stride=T * hw * c, bias=bias,
+             ntaps=3, tap_shift=hw, r1=r1.view(-1, c), s1=1.0, s0=0.5)
+    dense = dense.view(nb, T, hw, c)
+    for t0, tl in blocks:
+        pad = torch.zeros(nb, tl + 2, hw, c, device=DEV, dtype=torch.bfloat16)
+        lo, hi = max(t0 - 1, 0), min(t0 + tl + 1, T)
+        pad[:, lo - (t0 - 1): hi - (t0 - 1)] = a[:, lo:hi]            # halos from the neighbours, zeros at the ends
+        out = torch.empty(nb * tl * hw, c, device=DEV, dtype=torch.bfloat16)
+        r1l = r1[:, t0:t0 + tl].contiguous()
+        ops.gemm(pad.view(-1, c), w, out, K=c, N=c, rows_per_batch=tl * hw, batch=nb,
+                 a_batch_stride=(tl + 2) * hw * c, bias=bias, ntaps=3, tap_shift=hw, r1=r1l.view(-1, c), s1=1.0,
+                 s0=0.5, a_rows=(tl + 2) * hw, a_row0=hw)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(nb, tl, hw, c), dense[:, t0:t0 + tl]), f"block {(t0, tl)} differs from dense"
+
+
+@pytest.mark.parametrize("hw,heads,T,world", [(64, 5, 5, 2), (16, 20, 18, 8), (256, 10, 18, 4), (4, 1, 7, 3)])
+def test_temporal_attention_split_kv_equals_dense(hw, heads, T, world):
+    from v3d_b200 import ops
+    from v3d_b200.viewshard import ViewShard
+
+    nb, c = 2, heads * 64
+    g = torch.Generator(device=DEV).manual_seed(T * hw)
+    qkv = torch.randn(nb, T, hw, 3 * c, device=DEV, generator=g).to(torch.bfloat16)
+    dense = torch.empty(nb * T * hw, c, device=DEV, dtype=torch.bfloat16)
+    ops.attention_temporal(qkv.view(-1, 3 * c), dense, nb, T, hw, heads, 0.125)
+    dense = dense.view(nb, T, hw, c)
+    shards = [ViewShard(num_frames=T, rank=r, world=world) for r in range(world)]
+    tmax = shards[0].tmax
+    # what all_gather_into_tensor would deliver: rank-major slots of nb*tmax*hw rows, each filled from row 0
+    buf = torch.full((world * nb * tmax * hw, 2 * c), float("nan"), device=DEV, dtype=torch.bfloat16)
+    for vs in shards:
+        rows = nb * vs.tl * hw
+        buf[vs.rank * nb * tmax * hw: vs.rank * nb * tmax * hw + rows] = \
+            qkv[:, vs.frames].reshape(rows, 3 * c)[:, c:]
+    for vs in shards:
+        ql = qkv[:, vs.frames].reshape(nb * vs.tl * hw, 3 * c).contiguous()
+        out = torch.empty(nb * vs.tl * hw, c, device=DEV, dtype=torch.bfloat16)
+        row, bstride = vs.kv_table(nb, hw)
+        ops.attention_temporal_kv(ql, buf, out, nb, vs.tl, hw, heads, row, bstride, 0.125)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(nb, vs.tl, hw, c), dense[:, vs.frames]), f"rank {vs.rank} differs from dense"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# model level
+# --------------------------------------------------------------------------------------------------------------
+def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, T: int, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from oracle import synth  # seeded weights / inputs only (test infrastructure)
+    from v3d_b200 import engine
+    from v3d_b200.viewshard import ViewShard
+
+    dev = torch.device("cuda", 0 if one_gpu else rank)
+    torch.cuda.set_device(dev)
+    kw = {"device_id": dev} if backend == "nccl" else {}
+    dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    hw, steps = 16, 2
+    cfg = engine.v3d_512_config(num_frames=T, num_steps=steps, min_cfg=1.5, max_cfg=3.5)
+    cfg["network_config"]["params"]["model_channels"] = 64
+    cfg["first_stage_config"]["params"]["decoder_config"]["params"]["ch"] = 64
+    eng = engine.DiffusionEngine(**cfg)
+    unet, dec = eng.model.diffusion_model, eng.first_stage_model.decoder
+    unet.load_state_dict(synth.synth_state_dict(unet.param_shapes(), seed=11), strict=True)
+    dec.load_state_dict(synth.synth_state_dict(dec.param_shapes(), seed=12), strict=True)
+    eng = eng.to(dev).eval()
+    x, c, uc = synth.synth_inputs(T, hw)
+    to = lambda d: {k: v.to(dev) for k, v in d.items()}
+    c, uc = to(c), to(uc)
+    vs = ViewShard.create(T)
+    res = {"rank": rank, "block": (vs.t0, vs.tl)}
+
+    # one UNet forward, sharded vs unsharded
+    xin = torch.cat([torch.cat([x.to(dev)] * 2), torch.cat([uc["concat"], c["concat"]])], 1)   # [2T, 8, hw, hw]
+    ctx = torch.cat([uc["crossattn"], c["crossattn"]])
+    y = torch.cat([uc["vector"], c["vector"]])
+    ts = torch.full((2 * T,), 0.7, device=dev)
+    full = unet(xin, ts, ctx, y, None, T, torch.zeros(2, T, device=dev))
+    pick = torch.cat([torch.arange(vs.t0, vs.t0 + vs.tl), T + torch.arange(vs.t0, vs.t0 + vs.tl)]).to(dev)
+    unet.view_shard = vs
+    try:
+        part = unet(xin[pick], ts[pick], ctx[pick], y[pick], vs.time_context(c, uc), vs.tl,
+                    torch.zeros(2, vs.tl, device=dev))
+    finally:
+        unet.view_shard = None
+    res["unet_rel"] = _rel(part, full[pick])
+
+    # the whole hot path: sampler loop + decode
+    ref = eng.sample_views(x.clone().to(dev), c, uc, num_frames=T)
+    mine = eng.sample_views(x.clone().to(dev), c, uc, num_frames=T, view_shard=vs)
+    torch.cuda.synchronize()
+    res["frames_rel"] = _rel(mine, ref[vs.frames])
+    gathered = vs.gather_frames(mine)
+    res["gathered_rel"] = _rel(gathered, ref)
+    res["finite"] = bool(torch.isfinite(mine).all())
+    res["exchanges"] = dict(vs.exchanges)
+    q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_engine_pair(backend: str, one_gpu: bool, T: int = 5, world: int = 2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_engine_worker, args=(r, world, port, backend, one_gpu, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = sorted((q.get(timeout=900) for _ in range(world)), key=lambda r: r["rank"])
+    finally:
+        for p in procs:
+            p.join(timeout=120)
+            if p.is_alive():
+                p.kill()
+    for p in procs:
+        assert p.exitcode == 0
+    print(backend, res)
+    assert [r["block"] for r in res] == [(0, 3), (3, 2)]
+    for r in res:
+        assert r["finite"]
+        assert r["unet_rel"] <= 2e-3, r
+        assert r["frames_rel"] <= 5e-3 and r["gathered_rel"] <= 5e-3, r
+        # per forward: 2 norms + 2 halos per VideoResBlock, one K|V gather per SpatialVideoTransformer
+        assert r["exchanges"]["kv_allgather"] > 0 and r["exchanges"]["halo"] >= r["exchanges"]["gn_allreduce"] > 0
+
+
+def test_view_sharded_engine_matches_unsharded_one_gpu_gloo():
+    _run_engine_pair("gloo", one_gpu=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_view_sharded_engine_matches_unsharded_nccl():
+    _run_engine_pair("nccl", one_gpu=False)

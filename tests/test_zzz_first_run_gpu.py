@@ -1,0 +1,47 @@
+"""First hardware run of the GPU tests that were written after the round's GPU budget was spent.
+
+Those tests are skipped unless V3D_RUN_UNVALIDATED=1.  This file - collected last - runs them that way in CHILD
+processes under hard timeouts, so that a device fault in not-yet-seen code cannot poison the CUDA context of the
+validated suite; a failing child is reported as an expected failure (xfail, non-strict) with its output saved under
+gpurun_out/, a passing one as XPASS.  Once a group has passed on hardware its skip marker is removed and it leaves
+this list.  The CTA-pair GEMM test is not run from here (a cluster-barrier bug could hang the device): it stays a
+manual `V3D_RUN_UNVALIDATED=1 pytest -k cta_pair` under `timeout`.
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TESTS = Path(__file__).resolve().parent
+OUT = TESTS.parent / "gpurun_out"
+
+GROUPS = {
+    "kernels": [str(TESTS / "test_kernels_gpu.py"), "-k", "heun_step_kernel or concat_timestep_embedder"],
+    "parity": [str(TESTS / "test_parity_gpu.py"), "-k", "encoder or heun or vanilla or central"],
+    "viewshard_kernels": [str(TESTS / "test_viewshard_gpu.py"), "-k", "halo_mode or split_kv"],
+    "viewshard_engine": [str(TESTS / "test_viewshard_gpu.py"), "-k", "engine"],
+}
+
+
+@pytest.mark.parametrize("group", list(GROUPS))
+@pytest.mark.xfail(os.environ.get("V3D_RUN_UNVALIDATED") != "1", strict=False,
+                   reason="first hardware run of code written without GPU access")
+def test_first_hardware_run(group):
+    env = dict(os.environ, V3D_RUN_UNVALIDATED="1")
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", *GROUPS[group]]
+    try:
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1200)
+        text, rc = res.stdout[-6000:] + res.stderr[-3000:], res.returncode
+    except subprocess.TimeoutExpired as e:
+        text, rc = f"TIMEOUT after {e.timeout}s\n{(e.stdout or b'')[-3000:]!r}", 124
+    try:
+        OUT.mkdir(exist_ok=True)
+        (OUT / f"first_run_{group}.log").write_text(f"exit {rc}\n{text}")
+    except OSError:
+        pass
+    print(text)
+    assert rc == 0, f"{group}: exit {rc}\n{text}"
