@@ -90,6 +90,8 @@ typedef struct v3d_gemm_args {
 } v3d_gemm_args;
 
 int v3d_gemm_bf16(const v3d_gemm_args* args, void* stream);
+/* sizeof(v3d_gemm_args) as this library was compiled: bindings check their mirror of the struct against it. */
+int v3d_gemm_args_size(void);
 
 /* Permutation used to pack GEGLU projection rows so that each N-tile of width block_n holds
  * block_n/2 "value" rows followed by the matching block_n/2 "gate" rows

@@ -29,7 +29,9 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
     assert lib.v3d_abi_version() == 1
-    assert ctypes.sizeof(_lib.GemmArgs) == (7 * 8 + 8 * 8 + 16 * 4 + 3 * 4 + 7) // 8 * 8  # ptrs, i64s, i32s, f32s
+    # the ctypes mirror of v3d_gemm_args: 7 pointers, 8 int64, 16 int32, 3 floats, 2 int32 (halo fields), padded to 8
+    assert ctypes.sizeof(_lib.GemmArgs) == (7 * 8 + 8 * 8 + 16 * 4 + 3 * 4 + 2 * 4 + 7) // 8 * 8
+    assert lib.v3d_gemm_args_size() == ctypes.sizeof(_lib.GemmArgs)   # what the C side was compiled with
 
 
 def test_host_only_abi_functions():

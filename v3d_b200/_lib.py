@@ -44,6 +44,7 @@ SIGNATURES = {
     "v3d_last_error": (C.c_char_p, []),
     "v3d_launch_count": (C.c_int64, []),
     "v3d_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "v3d_gemm_args_size": (C.c_int, []),
     "v3d_geglu_pack_rows": (C.c_int, [_i32, _i32, C.POINTER(C.c_int32)]),
     "v3d_gemm_pick_block_n": (C.c_int, [_i32, _i32]),
     "v3d_debug_set_trace": (C.c_int, [_vp]),
@@ -102,6 +103,9 @@ def load():
         fn.argtypes = args
     if lib.v3d_abi_version() != 1:
         raise V3DLibraryError("libv3d_b200.so ABI version mismatch; rebuild")
+    if lib.v3d_gemm_args_size() != C.sizeof(GemmArgs):
+        raise V3DLibraryError(f"v3d_gemm_args is {lib.v3d_gemm_args_size()} bytes in libv3d_b200.so but "
+                              f"{C.sizeof(GemmArgs)} in the ctypes mirror; rebuild (python -m v3d_b200.build)")
     _lib = lib
     return lib
 

@@ -31,7 +31,6 @@ struct GemmEpi {
   long long ldd, ldr1, ldr2, ldfb;
   int batch, rows_per_batch, tiles_per_batch;
   int N, kpt, ntaps, tap_shift;  // kpt = K-blocks per tap
-  int tap0;  // A row coordinate of tap 0 relative to the output row: a_row0 - (ntaps / 2) * tap_shift
   int rows_per_frame, act, out_fp32;
   int b_batched;
   int fb_uniform;  // every 32-row warp slice of a tile lies in one frame: per-frame bias folds into the bias registers
@@ -44,6 +43,7 @@ struct GemmEpi {
   int cn, ch, cw, bw, bh, bn, tiles_w, tiles_h, bw_shift, bh_shift, tw_shift, th_shift;  // t*_shift < 0: not pow2
   int num_m_tiles, num_n_tiles;
   float s0, s1, s2;
+  int tap0;  // A row coordinate of tap 0 relative to the output row: a_row0 - (ntaps / 2) * tap_shift
 };
 
 // Diagnostics (role timelines through v3d_debug_set_trace, V3D_GEMM_DEBUG stage-skipping switches) are compiled in
@@ -790,6 +790,8 @@ extern "C" int v3d_geglu_pack_rows(int32_t n_out, int32_t block_n, int32_t* perm
   }
   return V3D_OK;
 }
+
+extern "C" int v3d_gemm_args_size(void) { return static_cast<int>(sizeof(v3d_gemm_args)); }
 
 extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
   if (a == nullptr || a->A == nullptr || a->B == nullptr || a->D == nullptr) {
