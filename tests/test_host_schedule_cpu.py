@@ -1,0 +1,181 @@
+"""The HOST SCHEDULES of the drop-in VideoUNet / VideoDecoder, executed on CPU with tests/emu_ops.py standing in for
+the C-ABI kernels (each stand-in restates one entry point's documented contract in torch).
+
+  * schedule vs oracle: every buffer, stride, fused-epilogue operand, packing permutation and layout decision of
+    `_run` must reproduce the reference arithmetic (oracle/ref_unet.py, oracle/ref_decoder.py) within the bf16
+    tolerance of SURVEY.md App. C (rel-L2 <= 3e-2, cosine >= 0.999);
+  * frame-sharded vs unsharded (2 ranks over gloo, uneven 3/2 split of T=5): the view-sharded schedule - halo'd
+    GroupNorm buffers, K|V gather + row table, time-context rows, frame-offset positional embedding, the decoder's
+    halo'd time_mix_conv - must agree with the unsharded schedule BIT FOR BIT (the stand-ins compute in fp64, so a
+    result does not depend on the shape a BLAS call happens to see; the only arithmetic difference left is the
+    summation order of the fp64 GroupNorm statistics, far below one bf16 ulp): rel-L2 <= 1e-6.
+The CUDA kernels themselves are checked on the GPU (tests/test_kernels_gpu.py, test_parity_gpu.py,
+test_viewshard_gpu.py); nothing here touches a device.
+"""
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = str(Path(__file__).resolve().parent.parent)
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+UNET_KW = dict(adm_in_channels=768, num_classes="sequential", use_checkpoint=True, in_channels=8, out_channels=4,
+               model_channels=64, attention_resolutions=[4, 2, 1], num_res_blocks=2, channel_mult=[1, 2, 4, 4],
+               num_head_channels=64, use_linear_in_transformer=True, transformer_depth=1, context_dim=1024,
+               spatial_transformer_attn_type="softmax-xformers", extra_ff_mix_layer=True, use_spatial_context=True,
+               merge_strategy="learned_with_images", video_kernel_size=[3, 1, 1])
+DEC_KW = dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64,
+              ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0, video_kernel_size=[3, 1, 1])
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def _cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-12)).item()
+
+
+def _build_unet():
+    from oracle import synth
+    from v3d_b200.unet import VideoUNet
+
+    net = VideoUNet(**UNET_KW)
+    sd = synth.synth_state_dict(net.param_shapes(), seed=11)
+    net.load_state_dict(sd, strict=True)
+    return net.eval(), sd
+
+
+def _build_decoder():
+    from oracle import synth
+    from v3d_b200.decoder import VideoDecoder
+
+    dec = VideoDecoder(**DEC_KW)
+    sd = synth.synth_state_dict(dec.param_shapes(), seed=12)
+    dec.load_state_dict(sd, strict=True)
+    return dec.eval(), sd
+
+
+def _unet_inputs(T, hw):
+    from oracle import synth
+
+    x, c, uc = synth.synth_inputs(T, hw)
+    # make the frames' contexts differ so that "frame 0 of each video" matters for the temporal cross-attention
+    g = torch.Generator().manual_seed(5)
+    c = dict(c, crossattn=c["crossattn"] + 0.5 * torch.randn(T, 1, 1024, generator=g))
+    xin = torch.cat([torch.cat([x, x]), torch.cat([uc["concat"], c["concat"]])], 1)
+    ctx = torch.cat([uc["crossattn"], c["crossattn"]])
+    y = torch.cat([uc["vector"], c["vector"]])
+    ts = torch.linspace(-0.5, 1.2, 2 * T)
+    return xin, ts, ctx, y
+
+
+def _run_unet(net, P, xin, ts, ctx2d, y, T):
+    B, _, H, W = xin.shape
+    with torch.no_grad():
+        return net._run(P, xin.float().contiguous(), ts.float().contiguous(), ctx2d.float().contiguous(),
+                        y.float().contiguous(), B, T, B // T, H, W, torch.device("cpu"))
+
+
+def test_unet_host_schedule_matches_oracle():
+    import emu_ops
+    from oracle import ref_unet
+
+    T, hw = 3, 16
+    net, sd = _build_unet()
+    xin, ts, ctx, y = _unet_inputs(T, hw)
+    with emu_ops.patched():
+        P = net._pack(torch.device("cpu"))
+        n0 = emu_ops.launch_count()
+        out = _run_unet(net, P, xin, ts, ctx.reshape(2 * T, -1), y, T)
+        launches = emu_ops.launch_count() - n0
+    with torch.no_grad():
+        ref = ref_unet.unet_forward(sd, ref_unet.UNetSpec(model_channels=64), xin, ts, ctx, y, T, torch.zeros(2, T))
+    r, cs = _rel(out, ref), _cos(out, ref)
+    print("unet schedule vs oracle: rel-L2", r, "cos", cs, "launches", launches)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert r <= 3e-2 and cs >= 0.999, (r, cs)
+    assert 600 < launches < 1400          # ~1.1k real launches; the stand-in counts a small_linear (prep + GEMM) once
+
+
+def test_decoder_host_schedule_matches_oracle():
+    import emu_ops
+    from oracle import ref_decoder
+
+    T, hw = 3, 8
+    dec, sd = _build_decoder()
+    z = torch.randn(T, 4, hw, hw, generator=torch.Generator().manual_seed(3))
+    with emu_ops.patched(), torch.no_grad():
+        P = dec._pack(torch.device("cpu"))
+        out = dec._run(P, z, T, T, 1, hw, hw)
+        ref = ref_decoder.decoder_forward(sd, ref_decoder.DecoderSpec(ch=64), z, T)
+    r, cs = _rel(out, ref), _cos(out, ref)
+    print("decoder schedule vs oracle: rel-L2", r, "cos", cs)
+    assert out.shape == ref.shape == (T, 3, 8 * hw, 8 * hw)
+    assert r <= 3e-2 and cs >= 0.999, (r, cs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# frame-sharded schedule vs unsharded schedule, 2 ranks over gloo
+# ---------------------------------------------------------------------------------------------------------------
+def _shard_worker(rank: int, world: int, port: int, T: int, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, str(Path(ROOT) / "tests"))
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    import emu_ops
+    from v3d_b200.viewshard import ViewShard
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    vs = ViewShard.create(T)
+    res = {"rank": rank, "block": (vs.t0, vs.tl)}
+    pick = torch.cat([torch.arange(vs.t0, vs.t0 + vs.tl), T + torch.arange(vs.t0, vs.t0 + vs.tl)])
+    with emu_ops.patched(), torch.no_grad():
+        net, _ = _build_unet()
+        P = net._pack(torch.device("cpu"))
+        xin, ts, ctx, y = _unet_inputs(T, 16)
+        full = _run_unet(net, P, xin, ts, ctx.reshape(2 * T, -1), y, T)
+        tc = torch.stack([ctx[0], ctx[T]])                               # frame 0 of the uc and the c video
+        net.view_shard = vs
+        try:
+            ctx_l = torch.cat([ctx[pick].reshape(2 * vs.tl, -1), tc.reshape(2, -1)])   # what forward() assembles
+            part = _run_unet(net, P, xin[pick], ts[pick], ctx_l, y[pick], vs.tl)
+        finally:
+            net.view_shard = None
+        res["unet_rel"] = _rel(part, full[pick])
+        res["unet_exchanges"] = dict(vs.exchanges)
+
+        dec, _ = _build_decoder()
+        Pd = dec._pack(torch.device("cpu"))
+        z = torch.randn(T, 4, 8, 8, generator=torch.Generator().manual_seed(3))   # the AttnBlock needs h*w % 64 == 0
+        full_d = dec._run(Pd, z, T, T, 1, 8, 8)
+        dec.view_shard = vs
+        try:
+            part_d = dec._run(Pd, z[vs.frames].contiguous(), vs.tl, vs.tl, 1, 8, 8)
+        finally:
+            dec.view_shard = None
+        res["dec_rel"] = _rel(part_d, full_d[vs.frames])
+        res["dec_gathered_rel"] = _rel(vs.gather_frames(part_d), full_d)
+    q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_host_schedule_matches_unsharded_gloo():
+    from mp_util import run_workers
+
+    world, T = 2, 5
+    res = sorted(run_workers(_shard_worker, world, (T,), timeout=900), key=lambda r: r["rank"])
+    print(res)
+    assert [r["block"] for r in res] == [(0, 3), (3, 2)]
+    for r in res:
+        assert r["unet_rel"] <= 1e-6, r
+        assert r["dec_rel"] <= 1e-6 and r["dec_gathered_rel"] <= 1e-6, r
+        # UNet: 22 VideoResBlocks x (2 statistics all-reduces + 2 halo exchanges), 16 transformers x 1 K|V gather
+        assert r["unet_exchanges"] == {"gn_allreduce": 44, "halo": 44, "kv_allgather": 16}, r

@@ -12,23 +12,15 @@ The arithmetic here is plain fp32 torch standing in for the kernels; the CUDA pa
 unsharded CUDA path in tests/test_viewshard_gpu.py.
 """
 import os
-import socket
 import sys
 from pathlib import Path
 
 import pytest
 import torch
-import torch.multiprocessing as mp
 import torch.nn.functional as F
 
 ROOT = str(Path(__file__).resolve().parent.parent)
 NB, C, HW, HEADS = 2, 64, 4, 1
-
-
-def _free_port() -> int:
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
 
 
 def _full_inputs(T: int):
@@ -140,16 +132,10 @@ def _worker(rank: int, world: int, port: int, T: int, q):
 
 @pytest.mark.parametrize("world,T", [(2, 5), (3, 7)])
 def test_view_shard_exchanges_match_unsharded(world, T):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, T, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=180) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    sys.path.insert(0, str(Path(ROOT) / "tests"))
+    from mp_util import run_workers
+
+    res = sorted(run_workers(_worker, world, (T,), timeout=180))
     covered = []
     for rank, (t0, tl), err, ok_gather, ok_cond, ok_tc, ok_guider, counts in res:
         covered += list(range(t0, t0 + tl))

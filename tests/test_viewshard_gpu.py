@@ -5,17 +5,18 @@ SAME BITS as the dense kernels on the frames they own (same K order, same tile a
 Model level: two processes run `DiffusionEngine.sample_views(view_shard=...)` on an uneven 3/2 split of T=5 frames
 and compare with the unsharded engine - over gloo with both ranks on cuda:0 (exchanges staged through the host, so it
 runs on a one-GPU box) and over NCCL on two GPUs when the box has them.  The only arithmetic difference is the
-summation order of the fp64 GroupNorm statistics, so the tolerance is far below the bf16 parity tolerance:
-rel-L2 <= 5e-3 on the decoded frames after 2 EDM steps, <= 2e-3 on one UNet forward.
+summation order of the fp64 GroupNorm statistics (atomics: the unsharded path is not run-to-run deterministic
+either); where that flips a bf16 rounding, this random-weight network amplifies the flip to its bf16 noise floor
+within a few blocks (measured with the CPU stand-ins: one flip -> rel-L2 1e-2 at the output), so the model-level
+bound is the parity tolerance of SURVEY.md App. C (rel-L2 <= 3e-2); the schedule itself is proven bit-exact against
+the unsharded schedule in tests/test_host_schedule_cpu.py and the kernels bit-exact above.
 """
 import os
-import socket
 import sys
 from pathlib import Path
 
 import pytest
 import torch
-import torch.multiprocessing as mp
 
 # first hardware run pending (written after the round-1 GPU budget was spent): enabled with V3D_RUN_UNVALIDATED=1;
 # tests/test_zzz_first_run_gpu.py runs this file that way in a child process at the end of the GPU suite
@@ -25,12 +26,6 @@ pytestmark = [pytest.mark.gpu,
 
 ROOT = str(Path(__file__).resolve().parent.parent)
 DEV = "cuda"
-
-
-def _free_port() -> int:
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
 
 
 def _rel(a, b):
@@ -159,27 +154,16 @@ def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool
 
 
 def _run_engine_pair(backend: str, one_gpu: bool, T: int = 5, world: int = 2):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_engine_worker, args=(r, world, port, backend, one_gpu, T, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    try:
-        res = sorted((q.get(timeout=900) for _ in range(world)), key=lambda r: r["rank"])
-    finally:
-        for p in procs:
-            p.join(timeout=120)
-            if p.is_alive():
-                p.kill()
-    for p in procs:
-        assert p.exitcode == 0
+    sys.path.insert(0, str(Path(ROOT) / "tests"))
+    from mp_util import run_workers
+
+    res = sorted(run_workers(_engine_worker, world, (backend, one_gpu, T), timeout=900), key=lambda r: r["rank"])
     print(backend, res)
     assert [r["block"] for r in res] == [(0, 3), (3, 2)]
     for r in res:
         assert r["finite"]
-        assert r["unet_rel"] <= 2e-3, r
-        assert r["frames_rel"] <= 5e-3 and r["gathered_rel"] <= 5e-3, r
+        assert r["unet_rel"] <= 3e-2, r
+        assert r["frames_rel"] <= 3e-2 and r["gathered_rel"] <= 3e-2, r
         # per forward: 2 norms + 2 halos per VideoResBlock, one K|V gather per SpatialVideoTransformer
         assert r["exchanges"]["kv_allgather"] > 0 and r["exchanges"]["halo"] >= r["exchanges"]["gn_allreduce"] > 0
 

@@ -211,8 +211,10 @@ def upsample_nearest2x(x: torch.Tensor, y: torch.Tensor, n: int, h: int, w: int,
     return y
 
 
-def copy_channels(src: torch.Tensor, ld_src: int, dst_ptr: int, ld_dst: int, rows: int, ncols: int) -> None:
-    _lib.check(_lib.load().v3d_copy_channels(src.data_ptr(), ld_src, dst_ptr, ld_dst, rows, ncols, _stream()),
+def copy_channels(src: torch.Tensor, ld_src: int, dst: torch.Tensor, ld_dst: int, rows: int, ncols: int) -> None:
+    """dst[r, :ncols] = src[r, :ncols] for `rows` rows of two row-strided bf16 buffers (`src` / `dst` may be column
+    slices of wider matrices: the views' data pointers carry the column offset, ld_* are the parents' row strides)."""
+    _lib.check(_lib.load().v3d_copy_channels(src.data_ptr(), ld_src, dst.data_ptr(), ld_dst, rows, ncols, _stream()),
                "v3d_copy_channels")
 
 

@@ -819,7 +819,7 @@ class VideoUNet(KernelModule):
             # frame-sharded: all-gather the packed K|V rows of every rank's frames, attend in place through the
             # per-frame row table; the time context (global frame 0 of each CFG half) is rows B.. of `cross`
             send = torch.empty(nb * vs.tmax * hw, 2 * c, device=dev, dtype=torch.bfloat16)
-            ops.copy_channels(qkv[:, c:], 3 * c, send.data_ptr(), 2 * c, rows, 2 * c)
+            ops.copy_channels(qkv[:, c:], 3 * c, send, 2 * c, rows, 2 * c)
             kv_row, kv_bstride = vs.kv_table(nb, hw)
             ops.attention_temporal_kv(qkv, vs.gather_rows(send), o, nb, T, hw, heads, kv_row, kv_bstride, scale)
             tc_bias, tc_ld = cross[B:, ot:], X
@@ -870,8 +870,8 @@ class VideoUNet(KernelModule):
                 skip, sc = saved.pop()
                 rows = B * h * w
                 cat = torch.empty(rows, ch + sc, device=dev, dtype=torch.bfloat16)
-                ops.copy_channels(cur, ch, cat.data_ptr(), ch + sc, rows, ch)
-                ops.copy_channels(skip, sc, cat.data_ptr() + ch * 2, ch + sc, rows, sc)
+                ops.copy_channels(cur, ch, cat, ch + sc, rows, ch)
+                ops.copy_channels(skip, sc, cat[:, ch:], ch + sc, rows, sc)
                 cur, ch = cat, ch + sc
             if self.debug_taps is not None and st.name in self.debug_taps and st.kind in ("res", "attn", "down", "up"):
                 tap = torch.empty(B, ch, h, w, device=dev, dtype=torch.float32)
