@@ -144,8 +144,9 @@ def _shard_worker(rank: int, world: int, port: int, T: int, q):
         tc = torch.stack([ctx[0], ctx[T]])                               # frame 0 of the uc and the c video
         net.view_shard = vs
         try:
-            ctx_l = torch.cat([ctx[pick].reshape(2 * vs.tl, -1), tc.reshape(2, -1)])   # what forward() assembles
-            part = _run_unet(net, P, xin[pick], ts[pick], ctx_l, y[pick], vs.tl)
+            # forward() minus its CUDA checks: argument assembly (time-context rows appended), then the schedule
+            args, dims, _ = net._prepare(xin[pick], ts[pick], ctx[pick], y[pick], tc, vs.tl, torch.zeros(2, vs.tl))
+            part = net._run(P, *args, *dims, torch.device("cpu"))
         finally:
             net.view_shard = None
         res["unet_rel"] = _rel(part, full[pick])
@@ -179,3 +180,23 @@ def test_view_sharded_host_schedule_matches_unsharded_gloo():
         assert r["dec_rel"] <= 1e-6 and r["dec_gathered_rel"] <= 1e-6, r
         # UNet: 22 VideoResBlocks x (2 statistics all-reduces + 2 halo exchanges), 16 transformers x 1 K|V gather
         assert r["unet_exchanges"] == {"gn_allreduce": 44, "halo": 44, "kv_allgather": 16}, r
+
+
+def test_encoder_host_schedule_matches_oracle():
+    """the native first-stage Encoder's schedule (asymmetric-pad stride-2 im2row, mid AttnBlock)."""
+    import emu_ops
+    from oracle import ref_encoder, synth
+    from v3d_b200.encoder import Encoder
+
+    enc = Encoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4, 4],
+                  num_res_blocks=2, attn_resolutions=[], dropout=0.0, attn_type="vanilla")
+    sd = synth.synth_state_dict(enc.param_shapes(), seed=13)
+    enc.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    with emu_ops.patched(), torch.no_grad():
+        out = enc.eval()._run(enc._pack(torch.device("cpu")), x)
+        ref = ref_encoder.encoder_forward(sd, ref_encoder.EncoderSpec(ch=64), x)
+    r, cs = _rel(out, ref), _cos(out, ref)
+    print("encoder schedule vs oracle: rel-L2", r, "cos", cs)
+    assert out.shape == ref.shape == (2, 8, 8, 8)
+    assert r <= 3e-2 and cs >= 0.999, (r, cs)

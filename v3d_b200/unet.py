@@ -640,14 +640,25 @@ class VideoUNet(KernelModule):
         num_video_frames: Optional[int] = None,
         image_only_indicator: Optional[torch.Tensor] = None,
     ) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("v3d_b200.VideoUNet.forward needs CUDA tensors; there is no CPU fallback")
+        args, dims, graphs = self._prepare(x, timesteps, context, y, time_context, num_video_frames,
+                                           image_only_indicator)
+        P = self.packed()
+        with torch.no_grad():
+            if graphs and self.debug_taps is None and not torch.cuda.is_current_stream_capturing():
+                return self._run_graphed(P, args, *dims, x.device)
+            return self._run(P, *args, *dims, x.device)
+
+    def _prepare(self, x, timesteps, context, y, time_context, num_video_frames, image_only_indicator):
+        """Argument checks of VideoUNet.forward (video_model.py:452-461) and assembly of the schedule's inputs:
+        -> ((x, timesteps, context rows, y) fp32 contiguous, (B, T, nb, H, W), use CUDA graphs)."""
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         assert y.shape[0] == x.shape[0]
         assert context is not None and context.ndim == 3, \
             f"n dims of spatial context should be 3 but are {None if context is None else context.ndim}"
         assert num_video_frames, "num_video_frames is required"
-        if not x.is_cuda:
-            raise RuntimeError("v3d_b200.VideoUNet.forward needs CUDA tensors; there is no CPU fallback")
         if context.shape[1] != 1:
             raise NotImplementedError("cross-attention context with more than one token is not implemented "
                                       "(V3D conditions on a single CLIP image token)")
@@ -656,7 +667,6 @@ class VideoUNet(KernelModule):
         assert B % T == 0 and cin == self.in_channels
         nb = B // T
         self._check_indicator(image_only_indicator, nb, T)
-        P = self.packed()
         dev = x.device
         ctx2d = context.float().reshape(B, -1)
         vs = self.view_shard
@@ -672,10 +682,7 @@ class VideoUNet(KernelModule):
             # collectives inside a captured graph are opt-in until validated on hardware
             graphs = graphs and os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1" and not vs._via_host(x)
         args = (x.float().contiguous(), timesteps.float().contiguous(), ctx2d.contiguous(), y.float().contiguous())
-        with torch.no_grad():
-            if graphs and self.debug_taps is None and not torch.cuda.is_current_stream_capturing():
-                return self._run_graphed(P, args, B, T, nb, H, W, dev)
-            return self._run(P, *args, B, T, nb, H, W, dev)
+        return args, (B, T, nb, H, W), graphs
 
     def _run_graphed(self, P, args, B, T, nb, H, W, dev):
         vs = self.view_shard
