@@ -338,7 +338,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       } else {
         const int m = o1 + tr;
         grow = static_cast<long long>(o0) * p.rows_per_batch + m;
-        return m < p.rows_per_batch;
+        // pair: with an odd number of 128-row tiles the peer's last tile lies past the last batch item (its TMA
+        // loads are zero-filled and its stores clipped; its residual / per-frame-bias rows must not be touched)
+        return m < p.rows_per_batch && (NCTA == 1 || o0 < p.batch);
       }
     };
     TileWalk tw(p, NCTA);
