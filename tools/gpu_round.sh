@@ -1,0 +1,67 @@
+#!/usr/bin/env bash
+# First GPU session of a round: what to run, in which order, with what time bound.  Every stage writes its log under
+# gpurun_out/ (merged back by gpurun) and is wrapped in `timeout`, so a hang in not-yet-validated code costs minutes,
+# not the box.  Usage (from the repo root, one stage list per gpurun call):
+#     gpurun --timeout 1500 -- 'bash tools/gpu_round.sh tests firstrun pair'
+#     gpurun --timeout 1200 -- 'bash tools/gpu_round.sh bench ncu_launches'
+#     gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_round.sh viewshard2'
+# Stages:
+#   tests         the validated GPU suite (pytest -m gpu; includes the first-run wrapper, which xfails on a child failure)
+#   firstrun      the not-yet-validated groups directly (V3D_RUN_UNVALIDATED=1), one child process each, verbose
+#   pair          cta_group::2 GEMM tiles (V3D_GEMM_2CTA=1) under a 300 s timeout, then the per-shape microbenchmark
+#                 with the switch off / on
+#   bench         bench.py (default N=1) -> gpurun_out/bench.json ; bench.py --impl reference -> bench_ref.json
+#   ncu_launches  the ncu launch list of one EDM step + decode (gpu__time_duration.sum, --clock-control none)
+#   ncu_full      ncu --set full of the named kernels (GEMM conv/geglu/proj, attention, GroupNorm, LayerNorm)
+#   viewshard2    (2 GPUs) NCCL engine parity test, then bench.py --shard views and --shard images at N=2
+set -u
+mkdir -p gpurun_out
+PY=python
+run() {  # run <seconds> <log> <cmd...>
+  local t=$1 log=$2; shift 2
+  echo "=== $* (timeout ${t}s) -> $log"
+  timeout "$t" "$@" > "gpurun_out/$log" 2>&1
+  local rc=$?
+  echo "exit $rc" >> "gpurun_out/$log"
+  tail -n 5 "gpurun_out/$log"
+  return 0
+}
+for stage in "$@"; do
+  case "$stage" in
+    tests)
+      run 1500 tests_gpu.log $PY -m pytest tests -m gpu -x -q ;;
+    firstrun)
+      export V3D_RUN_UNVALIDATED=1
+      run 300 first_kernels.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "heun_step_kernel or concat_timestep_embedder"
+      run 300 first_viewshard_kernels.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -k "halo_mode or split_kv"
+      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo"
+      run 900 first_parity.log $PY -m pytest tests/test_parity_gpu.py -m gpu -q -s -k "encoder or heun or vanilla or central"
+      unset V3D_RUN_UNVALIDATED ;;
+    pair)
+      V3D_RUN_UNVALIDATED=1 run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
+      run 300 micro_single.log $PY tools/microbench.py gemm conv
+      V3D_GEMM_2CTA=1 run 300 micro_pair.log $PY tools/microbench.py gemm conv ;;
+    bench)
+      run 900 bench.json $PY bench.py --steps 3 --warmup 3
+      run 900 bench_ref.json $PY bench.py --impl reference --steps 1 --warmup 1 ;;
+    bench_pair)
+      V3D_GEMM_2CTA=1 run 900 bench_pair.json $PY bench.py --steps 3 --warmup 3 --no-cpu-baseline ;;
+    ncu_launches)
+      V3D_CUDA_GRAPH=0 run 1200 ncu_launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
+        --log-file gpurun_out/launches.csv $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline ;;
+    ncu_full)
+      for k in gemm_tc_kernel attn_tc_kernel gn_stats_kernel gn_apply_kernel layernorm attn_temporal_kernel; do
+        V3D_CUDA_GRAPH=0 run 600 "ncu_full_$k.log" ncu --set full --clock-control none --import-source on \
+          -k "regex:$k" -s 40 -c 3 -o "gpurun_out/full_$k" -f $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline
+      done ;;
+    viewshard2)
+      V3D_RUN_UNVALIDATED=1 run 600 viewshard_nccl.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "nccl"
+      run 900 bench_views2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 2 --shard views --steps 3 --warmup 3
+      V3D_VIEWSHARD_GRAPH=1 run 900 bench_views2_graph.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+        --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --shard views --steps 3 --warmup 3
+      run 900 bench_images2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29513 bench.py --gpus 2 --steps 3 --warmup 3 ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
