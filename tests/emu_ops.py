@@ -289,10 +289,67 @@ def time_mix_conv(x, ldx, w, bias, y, nb, t, hw, c):
     return y
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# sampler arithmetic (fp32, elementwise; sampler.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _per_sample(v, like):
+    return v.float().reshape(-1, *([1] * (like.dim() - 1)))
+
+
+def edm_scale_input(x, sigma, y, c_noise, nsamples, per_sample):
+    _tick()
+    s = _per_sample(sigma, x)
+    y.copy_(x * (1.0 / torch.sqrt(s * s + 1.0)))
+    if c_noise is not None:
+        c_noise.copy_(0.25 * torch.log(sigma.float()).reshape(c_noise.shape))
+    return y
+
+
+def edm_denoise_combine(net, x, sigma, out, nsamples, per_sample):
+    _tick()
+    s = _per_sample(sigma, x)
+    d = s * s + 1.0
+    out.copy_(net * (-s / torch.sqrt(d)) + x * (1.0 / d))
+    return out
+
+
+def cfg_combine(den, scale, out, b, t, per_sample):
+    _tick()
+    half = b * t
+    xu, xc = den[:half], den[half:]
+    sc = scale.float().reshape(-1)[:t].repeat(b).reshape(half, *([1] * (den.dim() - 1)))
+    out.copy_(xu + sc * (xc - xu))
+    return out
+
+
+def euler_step(x, den, sigma_hat, sigma_next, out, nsamples, per_sample):
+    _tick()
+    sh, sn = _per_sample(sigma_hat, x), _per_sample(sigma_next, x)
+    out.copy_(x + (sn - sh) * ((x - den) / sh))
+    return out
+
+
+def heun_step(x, den, x_euler, den2, sigma_hat, sigma_next, out, nsamples, per_sample):
+    _tick()
+    sh, sn = _per_sample(sigma_hat, x), _per_sample(sigma_next, x)
+    d = (x - den) / sh
+    d2 = (x_euler - den2) / sn.clamp_min(1e-30)
+    out.copy_(torch.where(sn > 0, x + ((d + d2) / 2.0) * (sn - sh), x_euler))
+    return out
+
+
+def frames_nchw_to_u8(x, y):
+    _tick()
+    v = torch.clamp((x.float() + 1.0) / 2.0, 0.0, 1.0) * 255.0
+    y.copy_(v.permute(0, 2, 3, 1).to(torch.uint8))                  # truncating cast, like numpy astype
+    return y
+
+
 _EMULATED = ["launch_count", "gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "softmax_rows_f32",
              "attention_spatial", "attention_temporal", "attention_temporal_kv", "upsample_nearest2x", "copy_channels",
              "im2col3x3", "nchw_f32_to_nhwc_bf16", "nhwc_to_nchw_f32", "small_linear", "timestep_embedding",
-             "time_mix_conv"]
+             "time_mix_conv", "edm_scale_input", "edm_denoise_combine", "cfg_combine", "euler_step", "heun_step",
+             "frames_nchw_to_u8"]
 
 
 @contextlib.contextmanager

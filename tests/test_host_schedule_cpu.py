@@ -200,3 +200,83 @@ def test_encoder_host_schedule_matches_oracle():
     print("encoder schedule vs oracle: rel-L2", r, "cos", cs)
     assert out.shape == ref.shape == (2, 8, 8, 8)
     assert r <= 3e-2 and cs >= 0.999, (r, cs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the whole hot path (DiffusionEngine.sample_views: sampler loop + CFG + denoiser + UNet + decode) on CPU
+# ---------------------------------------------------------------------------------------------------------------
+def test_sample_views_host_path_matches_oracle():
+    """What __graft_entry__.smoke() checks on the GPU, with the kernels replaced by their CPU stand-ins: 2 Euler-EDM
+    steps with per-frame CFG scales through the drop-in sampler / guider / denoiser / wrapper / UNet, then the decode."""
+    import cpu_shims
+    import emu_ops
+    from oracle import ref_decoder, ref_sampling, ref_unet, synth
+
+    T, hw, steps = 3, 8, 2
+    eng, sd_u, sd_d = cpu_shims.cpu_engine(T, steps)
+    x, c, uc = synth.synth_inputs(T, hw)
+    with emu_ops.patched():
+        frames = eng.sample_views(x.clone(), c, uc, num_frames=T)
+        u8 = emu_ops.frames_nchw_to_u8(frames, torch.empty(T, 8 * hw, 8 * hw, 3, dtype=torch.uint8))
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    with torch.no_grad():
+        z_ref = ref_sampling.euler_edm_sample(
+            lambda i, s, cc: ref_sampling.denoiser(
+                lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd_u, ref_unet.UNetSpec(model_channels=64), xx, tt,
+                                                                   cond, **kw), i, s, cc, **extra),
+            x.clone(), c, uc, steps, ref_sampling.guider_scale(1.5, 3.5, T), T)
+        img_ref = ref_decoder.decode_first_stage(sd_d, ref_decoder.DecoderSpec(ch=64), z_ref, n_samples_a_time=T)
+    r, cs = _rel(frames, img_ref), _cos(frames, img_ref)
+    print("sample_views host path vs oracle: rel-L2", r, "cos", cs)
+    assert frames.shape == img_ref.shape == (T, 3, 8 * hw, 8 * hw) and torch.isfinite(frames).all()
+    assert r <= 5e-2 and cs >= 0.998, (r, cs)                      # the bound smoke() applies on the GPU
+    ref_u8 = (torch.clamp((frames + 1.0) / 2.0, 0.0, 1.0) * 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(u8, ref_u8)                                  # V3D_512.py:286-303 wire format
+
+
+def _engine_shard_worker(rank: int, world: int, port: int, T: int, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, str(Path(ROOT) / "tests"))
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    import cpu_shims
+    import emu_ops
+    from oracle import synth
+    from v3d_b200.viewshard import ViewShard
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    vs = ViewShard.create(T)
+    eng, _, _ = cpu_shims.cpu_engine(T, 2)
+    x, c, uc = synth.synth_inputs(T, 8)
+    g = torch.Generator().manual_seed(5)
+    c = dict(c, crossattn=c["crossattn"] + 0.5 * torch.randn(T, 1, 1024, generator=g))   # frames differ
+    with emu_ops.patched():
+        ref = eng.sample_views(x.clone(), c, uc, num_frames=T)
+        mine = eng.sample_views(x.clone(), c, uc, num_frames=T, view_shard=vs)
+        gathered = vs.gather_frames(mine)
+    q.put({"rank": rank, "block": (vs.t0, vs.tl), "local_rel": _rel(mine, ref[vs.frames]),
+           "gathered_rel": _rel(gathered, ref), "shape": tuple(mine.shape), "exchanges": dict(vs.exchanges),
+           "guider_frames": eng.sampler.guider.num_frames, "hooks_cleared":
+               eng.model.diffusion_model.view_shard is None and eng.first_stage_model.decoder.view_shard is None})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_sample_views_matches_unsharded_gloo():
+    """DiffusionEngine.sample_views(view_shard=...) end to end (cond slicing, guider slice, time context, sampler
+    state per block, sharded UNet x 2 steps x CFG, sharded decode, frame gather) == the unsharded call, bit for bit."""
+    from mp_util import run_workers
+
+    world, T = 2, 5
+    res = sorted(run_workers(_engine_shard_worker, world, (T,), timeout=900), key=lambda r: r["rank"])
+    print(res)
+    assert [r["block"] for r in res] == [(0, 3), (3, 2)]
+    for r in res:
+        assert r["shape"] == (r["block"][1], 3, 64, 64)
+        assert r["local_rel"] <= 1e-6 and r["gathered_rel"] <= 1e-6, r
+        assert r["guider_frames"] == T and r["hooks_cleared"], r        # the engine's own sampler is left untouched
+        # 2 EDM steps x one CFG-batched forward: 2 x (44 + 44 + 16); decode: 28 norms, 29 halos; one frame gather
+        assert r["exchanges"] == {"gn_allreduce": 88 + 28, "halo": 88 + 29, "kv_allgather": 32, "frame_gather": 1}, r

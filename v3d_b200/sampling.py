@@ -261,6 +261,10 @@ class EulerEDMSampler:
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
         if not x.is_cuda:
             raise RuntimeError("v3d_b200.EulerEDMSampler needs CUDA tensors; there is no CPU fallback")
+        return self._loop(denoiser, x, cond, uc, num_steps)
+
+    def _loop(self, denoiser, x, cond, uc=None, num_steps=None):
+        """EDMSampler.__call__ (sampling.py:112-133) below the CUDA check."""
         assert x.dtype == torch.float32, "sampler state is fp32 (denoiser.py:36-39)"
         x, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
         n = x.shape[0]
@@ -307,6 +311,9 @@ class HeunEDMSampler(EulerEDMSampler):
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
         if not x.is_cuda:
             raise RuntimeError("v3d_b200.HeunEDMSampler needs CUDA tensors; there is no CPU fallback")
+        return self._loop(denoiser, x, cond, uc, num_steps)
+
+    def _loop(self, denoiser, x, cond, uc=None, num_steps=None):
         assert x.dtype == torch.float32, "sampler state is fp32 (denoiser.py:36-39)"
         x, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
         n = x.shape[0]
