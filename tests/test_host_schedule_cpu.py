@@ -16,6 +16,7 @@ import os
 import sys
 from pathlib import Path
 
+import pytest
 import torch
 
 ROOT = str(Path(__file__).resolve().parent.parent)
@@ -280,3 +281,114 @@ def test_view_sharded_sample_views_matches_unsharded_gloo():
         assert r["guider_frames"] == T and r["hooks_cleared"], r        # the engine's own sampler is left untouched
         # 2 EDM steps x one CFG-batched forward: 2 x (44 + 44 + 16); decode: 28 norms, 29 halos; one frame gather
         assert r["exchanges"] == {"gn_allreduce": 88 + 28, "halo": 88 + 29, "kv_allgather": 32, "frame_gather": 1}, r
+
+
+@pytest.mark.parametrize("tag", ["edm_small", "edm_small_heun", "edm_small_central", "edm_small_vanilla"])
+def test_sampler_variants_host_path_match_reference_golden(tag):
+    """EulerEDMSampler / HeunEDMSampler x LinearPrediction / CentralPrediction / VanillaCFG guiders
+    through the drop-in classes with the kernels' CPU stand-ins, against the REAL reference's outputs
+    (tests/golden/edm_small*.pt, 3 steps at latent 32; bound = the GPU parity tolerance, rel-L2 <= 3e-2)."""
+    import json
+
+    import cpu_shims
+    import emu_ops
+    from oracle import synth
+    from v3d_b200 import sampling
+    from v3d_b200.unet import VideoUNet
+
+    gold_dir = Path(ROOT) / "tests" / "golden"
+    manifest = json.loads((gold_dir / "MANIFEST.json").read_text())
+    m, mu = manifest[tag], manifest["unet_small"]
+    gold = torch.load(gold_dir / f"{tag}.pt")
+    net = VideoUNet(**dict(UNET_KW, model_channels=mu["model_channels"]))
+    net.load_state_dict(synth.synth_state_dict(net.param_shapes(), seed=mu["weight_seed"]), strict=True)
+    net.__class__ = cpu_shims.CpuUNet
+    T, hw = m["T"], m["latent_hw"]
+    x, c, uc = synth.synth_inputs(T, hw)
+    base = "v3d_b200.sgm.modules.diffusionmodules."
+    kind = m.get("guider", "linear")
+    guider = {"linear": {"target": base + "guiders.LinearPredictionGuider",
+                         "params": {"max_scale": m["max_scale"], "min_scale": m["min_scale"], "num_frames": T}},
+              "central": {"target": base + "guiders.CentralPredictionGuider",
+                          "params": {"max_scale": m["max_scale"], "min_scale": m["min_scale"], "num_frames": T}},
+              "vanilla": {"target": base + "guiders.VanillaCFG", "params": {"scale": m.get("vanilla_scale", 2.5)}}}[kind]
+    shim = {"EulerEDMSampler": cpu_shims.CpuEuler, "HeunEDMSampler": cpu_shims.CpuHeun}[m.get("sampler", "EulerEDMSampler")]
+    sampler = shim(num_steps=m["num_steps"],
+                   discretization_config={"target": base + "discretizer.EDMDiscretization",
+                                          "params": {"sigma_max": m["sigma_max"]}}, guider_config=guider)
+    den = sampling.Denoiser({"target": base + "denoiser_scaling.VScalingWithEDMcNoise"})
+    model = sampling.OpenAIWrapper(net.eval())
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    x0 = x.clone()
+    with emu_ops.patched():
+        n0 = emu_ops.launch_count()
+        out = sampler(lambda i, s, cc: den(model, i, s, cc, **extra), x0, cond=c, uc=uc)
+        launches = emu_ops.launch_count() - n0
+    r = _rel(out, gold["out"])
+    print(tag, "host path vs reference golden: rel-L2", r, "launches", launches)
+    assert not torch.equal(x0, x)                       # the caller's noise is scaled in place, like sampling.py:50
+    # Three Heun steps down from sigma = 700 are an unstable integration (reference output std 14 against 1.4 for
+    # Euler): they amplify the network's bf16 rounding (measured 9e-2 with the stand-ins) although the sampler logic
+    # is exact (next test).  The Euler variants stay inside the usual parity bound.
+    assert r <= (2e-1 if "heun" in tag else 3e-2), (tag, r)
+
+
+@pytest.mark.parametrize("tag", ["edm_small", "edm_small_heun", "edm_small_central", "edm_small_vanilla"])
+def test_sampler_variants_logic_exact_with_fp32_network(tag):
+    """The drop-in samplers / guiders / denoiser (their elementwise kernels as CPU stand-ins) around the ORACLE's
+    fp32 UNet reproduce the real reference's outputs to fp32 rounding: schedule, CFG batch order, per-frame scales,
+    Heun's second evaluation and its first-order last step are all exactly the reference's."""
+    import json
+
+    import cpu_shims
+    import emu_ops
+    from oracle import ref_unet, synth
+    from v3d_b200 import sampling
+
+    gold_dir = Path(ROOT) / "tests" / "golden"
+    manifest = json.loads((gold_dir / "MANIFEST.json").read_text())
+    m, mu = manifest[tag], manifest["unet_small"]
+    gold = torch.load(gold_dir / f"{tag}.pt")
+    spec = ref_unet.UNetSpec(model_channels=mu["model_channels"])
+    sd = synth.synth_state_dict(ref_unet.unet_param_shapes(spec), seed=mu["weight_seed"])
+    T, hw = m["T"], m["latent_hw"]
+    x, c, uc = synth.synth_inputs(T, hw)
+    base = "v3d_b200.sgm.modules.diffusionmodules."
+    kind = m.get("guider", "linear")
+    guider = {"linear": {"target": base + "guiders.LinearPredictionGuider",
+                         "params": {"max_scale": m["max_scale"], "min_scale": m["min_scale"], "num_frames": T}},
+              "central": {"target": base + "guiders.CentralPredictionGuider",
+                          "params": {"max_scale": m["max_scale"], "min_scale": m["min_scale"], "num_frames": T}},
+              "vanilla": {"target": base + "guiders.VanillaCFG", "params": {"scale": m.get("vanilla_scale", 2.5)}}}[kind]
+    shim = {"EulerEDMSampler": cpu_shims.CpuEuler, "HeunEDMSampler": cpu_shims.CpuHeun}[m.get("sampler", "EulerEDMSampler")]
+    sampler = shim(num_steps=m["num_steps"],
+                   discretization_config={"target": base + "discretizer.EDMDiscretization",
+                                          "params": {"sigma_max": m["sigma_max"]}}, guider_config=guider)
+    den = sampling.Denoiser({"target": base + "denoiser_scaling.VScalingWithEDMcNoise"})
+
+    class OracleNet(torch.nn.Module):
+        def forward(self, xx, t, cond, **kw):
+            with torch.no_grad():
+                return ref_unet.openai_wrapper(sd, spec, xx, t, cond, **kw)
+
+    extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+    with emu_ops.patched():
+        out = sampler(lambda i, s, cc: den(OracleNet(), i, s, cc, **extra), x.clone(), cond=c, uc=uc)
+    r = _rel(out, gold["out"])
+    print(tag, "sampler logic with fp32 network vs reference golden: rel-L2", r)
+    assert r <= 1e-5, (tag, r)
+
+
+def test_conditioning_host_path_matches_reference_golden():
+    """GeneralConditioner / ConcatTimestepEmbedderND / get_batch assembly (scripts/pub/V3D_512.py:247-267)
+    through the drop-in module with v3d_timestep_embedding's stand-in, against the real reference's (c, uc)."""
+    import emu_ops
+    from v3d_b200 import conditioning
+
+    gold = torch.load(Path(ROOT) / "tests" / "golden" / "conditioning.pt")
+    with emu_ops.patched():
+        cond = conditioning.GeneralConditioner(conditioning.V3D_512_EMB_MODELS)
+        c, uc = conditioning.assemble_v3d_conditioning(cond, gold["clip_emb"], gold["latent"], 6.0, 127.0, 0.02, 18)
+    assert torch.allclose(c["vector"], gold["c"]["vector"], atol=2e-6) and torch.equal(uc["vector"], c["vector"])
+    assert torch.equal(c["crossattn"], gold["c"]["crossattn"]) and torch.equal(uc["concat"], gold["uc"]["concat"])
+    assert torch.equal(c["concat"], gold["c"]["concat"]) and torch.equal(uc["crossattn"], gold["uc"]["crossattn"])
