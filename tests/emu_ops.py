@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import contextlib
 import math
-from typing import Optional
 
 import torch
 import torch.nn.functional as F
