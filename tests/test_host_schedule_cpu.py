@@ -392,3 +392,22 @@ def test_conditioning_host_path_matches_reference_golden():
     assert torch.allclose(c["vector"], gold["c"]["vector"], atol=2e-6) and torch.equal(uc["vector"], c["vector"])
     assert torch.equal(c["crossattn"], gold["c"]["crossattn"]) and torch.equal(uc["concat"], gold["uc"]["concat"])
     assert torch.equal(c["concat"], gold["c"]["concat"]) and torch.equal(uc["crossattn"], gold["uc"]["crossattn"])
+
+
+def test_single_rank_view_shard_schedule_equals_unsharded():
+    """world = 1: the frame-sharded schedule (halo'd GroupNorm buffers with zero halos, split-KV attention over its own
+    frames, statistics rescaled by 1, halo'd time_mix_conv) needs no process group and must equal the dense schedule."""
+    import cpu_shims
+    import emu_ops
+    from oracle import synth
+    from v3d_b200.viewshard import ViewShard
+
+    T = 3
+    eng, _, _ = cpu_shims.cpu_engine(T, 2)
+    x, c, uc = synth.synth_inputs(T, 8)
+    vs = ViewShard(num_frames=T, rank=0, world=1)
+    with emu_ops.patched():
+        ref = eng.sample_views(x.clone(), c, uc, num_frames=T)
+        one = eng.sample_views(x.clone(), c, uc, num_frames=T, view_shard=vs)
+    assert torch.equal(one, ref)
+    assert vs.exchanges["halo"] == 2 * 44 + 29 and vs.exchanges["kv_allgather"] == 32

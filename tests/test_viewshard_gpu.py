@@ -92,6 +92,34 @@ def test_temporal_attention_split_kv_equals_dense(hw, heads, T, world):
         assert torch.equal(out.view(nb, vs.tl, hw, c), dense[:, vs.frames]), f"rank {vs.rank} differs from dense"
 
 
+def test_single_rank_view_shard_equals_unsharded_engine():
+    """world = 1 needs no process group: the frame-sharded code path (halo'd operands with zero halos, split-KV
+    attention over its own frames, halo'd time_mix_conv) on one GPU must reproduce the dense path."""
+    sys.path.insert(0, ROOT)
+    from oracle import synth  # seeded weights / inputs only
+    from v3d_b200 import engine
+    from v3d_b200.viewshard import ViewShard
+
+    T, hw = 5, 16
+    cfg = engine.v3d_512_config(num_frames=T, num_steps=2, min_cfg=1.5, max_cfg=3.5)
+    cfg["network_config"]["params"]["model_channels"] = 64
+    cfg["first_stage_config"]["params"]["decoder_config"]["params"]["ch"] = 64
+    eng = engine.DiffusionEngine(**cfg)
+    unet, dec = eng.model.diffusion_model, eng.first_stage_model.decoder
+    unet.load_state_dict(synth.synth_state_dict(unet.param_shapes(), seed=11), strict=True)
+    dec.load_state_dict(synth.synth_state_dict(dec.param_shapes(), seed=12), strict=True)
+    eng = eng.to(DEV).eval()
+    x, c, uc = synth.synth_inputs(T, hw)
+    c, uc = {k: v.to(DEV) for k, v in c.items()}, {k: v.to(DEV) for k, v in uc.items()}
+    vs = ViewShard(num_frames=T, rank=0, world=1)
+    ref = eng.sample_views(x.clone().to(DEV), c, uc, num_frames=T)
+    one = eng.sample_views(x.clone().to(DEV), c, uc, num_frames=T, view_shard=vs)
+    torch.cuda.synchronize()
+    r = _rel(one, ref)
+    print("world-1 shard vs dense: rel-L2", r, vs.exchanges)
+    assert torch.isfinite(one).all() and r <= 3e-2, r      # fp64-atomic statistics order is the only difference
+
+
 # --------------------------------------------------------------------------------------------------------------
 # model level
 # --------------------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ GROUPS = {
     "parity": [str(TESTS / "test_parity_gpu.py"), "-k", "encoder or heun or vanilla or central"],
     "viewshard_kernels": [str(TESTS / "test_viewshard_gpu.py"), "-k", "halo_mode or split_kv"],
     "viewshard_engine": [str(TESTS / "test_viewshard_gpu.py"), "-k", "engine"],
+    "fullsize_properties": [str(TESTS / "test_fullsize_gpu.py")],
 }
 
 

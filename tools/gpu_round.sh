@@ -34,8 +34,9 @@ for stage in "$@"; do
       export V3D_RUN_UNVALIDATED=1
       run 300 first_kernels.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "heun_step_kernel or concat_timestep_embedder"
       run 300 first_viewshard_kernels.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -k "halo_mode or split_kv"
-      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo"
+      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo or single_rank"
       run 900 first_parity.log $PY -m pytest tests/test_parity_gpu.py -m gpu -q -s -k "encoder or heun or vanilla or central"
+      run 900 first_fullsize.log $PY -m pytest tests/test_fullsize_gpu.py -m gpu -q -s
       unset V3D_RUN_UNVALIDATED ;;
     pair)
       V3D_RUN_UNVALIDATED=1 run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
