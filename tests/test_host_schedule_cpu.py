@@ -411,3 +411,56 @@ def test_single_rank_view_shard_schedule_equals_unsharded():
         one = eng.sample_views(x.clone(), c, uc, num_frames=T, view_shard=vs)
     assert torch.equal(one, ref)
     assert vs.exchanges["halo"] == 2 * 44 + 29 and vs.exchanges["kv_allgather"] == 32
+
+
+def _plan_worker(rank: int, world: int, port: int, T: int, mode: str, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, str(Path(ROOT) / "tests"))
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    import cpu_shims
+    import emu_ops
+    from oracle import synth
+    from v3d_b200.viewshard import ShardPlan
+
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = ShardPlan.create(T, mode)
+    eng, _, _ = cpu_shims.cpu_engine(T, 2)
+    x, c, uc = synth.synth_inputs(T, 8)
+    g = torch.Generator().manual_seed(5)
+    c = dict(c, crossattn=c["crossattn"] + 0.5 * torch.randn(T, 1, 1024, generator=g))
+    with emu_ops.patched():
+        ref = eng.sample_views(x.clone(), c, uc, num_frames=T)
+        mine = eng.sample_views(x.clone(), c, uc, num_frames=T, shard=plan)
+        gathered = plan.gather_frames(mine)
+    q.put({"rank": rank, "decode_block": (plan.decode.t0, plan.decode.tl),
+           "local_rel": _rel(mine, ref[plan.decode.frames]), "gathered_rel": _rel(gathered, ref),
+           "plan": plan.describe()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,world,T", [("cfg", 2, 4), ("cfg+views", 4, 5)])
+def test_cfg_split_plans_match_unsharded_gloo(mode, world, T):
+    """ShardPlan 'cfg' (the [uc; c] halves on two ranks, one all-gather per network evaluation, decode on two frame
+    blocks) and 'cfg+views' (frame blocks x CFG pairs, decode blocks nested in the sampling blocks) reproduce the
+    unsharded DiffusionEngine.sample_views bit for bit."""
+    from mp_util import run_workers
+
+    res = sorted(run_workers(_plan_worker, world, (T, mode), timeout=900), key=lambda r: r["rank"])
+    print(res)
+    covered = []
+    for r in res:
+        covered += list(range(r["decode_block"][0], sum(r["decode_block"])))
+        assert r["local_rel"] <= 1e-6 and r["gathered_rel"] <= 1e-6, r
+        assert r["plan"]["exchanges"]["cfg_gather"] == 2              # 2 EDM steps x one network evaluation
+    assert covered == list(range(T))
+    if mode == "cfg":
+        assert all("halo" not in r["plan"]["exchanges"] for r in res)  # the UNet runs dense on each CFG half
+        assert [r["plan"]["cfg_rank"] for r in res] == [0, 1]
+    else:
+        assert [r["plan"]["sample_blocks"] for r in res] == [[(0, 3), (3, 2)]] * 4
+        assert [r["decode_block"] for r in res] == [(0, 2), (2, 1), (3, 1), (4, 1)]

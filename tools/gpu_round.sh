@@ -34,7 +34,7 @@ for stage in "$@"; do
       export V3D_RUN_UNVALIDATED=1
       run 300 first_kernels.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "heun_step_kernel or concat_timestep_embedder"
       run 300 first_viewshard_kernels.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -k "halo_mode or split_kv"
-      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo or single_rank"
+      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo or single_rank"   # incl. the cfg / cfg+views plans
       run 900 first_parity.log $PY -m pytest tests/test_parity_gpu.py -m gpu -q -s -k "encoder or heun or vanilla or central"
       run 900 first_fullsize.log $PY -m pytest tests/test_fullsize_gpu.py -m gpu -q -s
       unset V3D_RUN_UNVALIDATED ;;
@@ -61,6 +61,8 @@ for stage in "$@"; do
         --master-port 29511 bench.py --gpus 2 --shard views --steps 3 --warmup 3
       V3D_VIEWSHARD_GRAPH=1 run 900 bench_views2_graph.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
         --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --shard views --steps 3 --warmup 3
+      run 900 bench_cfg2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29514 bench.py --gpus 2 --shard cfg --steps 3 --warmup 3
       run 900 bench_images2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29513 bench.py --gpus 2 --steps 3 --warmup 3 ;;
     *) echo "unknown stage $stage" ;;

@@ -122,14 +122,20 @@ class DiffusionEngine(nn.Module):
 
     @torch.no_grad()
     def sample_views(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int,
-                     decoding_t: Optional[int] = None, view_shard=None) -> torch.Tensor:
+                     decoding_t: Optional[int] = None, view_shard=None, shard=None) -> torch.Tensor:
         """The hot path of sample_one (scripts/pub/V3D_512.py:269-285): sampler loop + first-stage decode.
         randn [T,4,h,w] fp32 (scaled in place, as in the reference); returns [T,3,8h,8w] fp32.
 
-        `view_shard` (v3d_b200.viewshard.ViewShard): every rank passes the SAME full-video randn / c / uc and gets
-        back the decoded frames of its own block [tl,3,8h,8w] (`view_shard.gather_frames` assembles the video)."""
-        if view_shard is not None:
-            return self._sample_views_sharded(randn, c, uc, num_frames, view_shard)
+        ONE image over several ranks: `shard` = a v3d_b200.viewshard.ShardPlan (frame blocks, CFG-pair split, or both;
+        `view_shard=ViewShard` is shorthand for the frame-block plan).  Every rank passes the SAME full-video randn / c /
+        uc and gets back the decoded frames of its own block [t_local,3,8h,8w]; `gather_frames` of the plan (or of the
+        ViewShard) assembles the video.  The video is decoded as one chunk (decoding_t = T)."""
+        if view_shard is not None and shard is None:
+            from .viewshard import ShardPlan
+
+            shard = ShardPlan("views", num_frames, view_shard, None, view_shard)
+        if shard is not None:
+            return self._sample_views_sharded(randn, c, uc, num_frames, shard)
         extra = {"image_only_indicator": torch.zeros(2, num_frames, device=randn.device),
                  "num_video_frames": num_frames}
 
@@ -141,26 +147,41 @@ class DiffusionEngine(nn.Module):
         return self.decode_first_stage(samples_z)
 
     @torch.no_grad()
-    def _sample_views_sharded(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int, vs) -> torch.Tensor:
-        """One image, T view-frames split across the ranks of `vs`.  The sampler state, the CFG pair
-        and the Euler update of a frame stay on its rank; the UNet and the decoder exchange K|V, conv halos and 3-D
-        GroupNorm statistics through `vs`.  The video is decoded as one chunk (decoding_t = T)."""
-        assert vs.num_frames == num_frames and randn.shape[0] == num_frames
+    def _sample_views_sharded(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int, plan) -> torch.Tensor:
+        """One image spread over ranks.  Frame blocks: the sampler state, the CFG pair and the Euler
+        update of a frame stay on its rank, the UNet exchanges K|V, conv halos and 3-D GroupNorm statistics.  CFG split:
+        each rank of a pair runs the network on one half of [uc; c] and the halves are all-gathered before the
+        guidance.  The decode always runs on frame blocks (`plan.decode`)."""
+        from .viewshard import CfgSplitGuider
+
+        vs, cs, dvs = plan.sample, plan.cfg, plan.decode
+        assert plan.num_frames == num_frames and randn.shape[0] == num_frames
         unet = self.model.diffusion_model
         decoder = self.first_stage_model.decoder
-        x = randn[vs.frames].clone()
-        c_l, uc_l = vs.shard_cond(c), vs.shard_cond(uc)
-        extra = {"image_only_indicator": torch.zeros(2, vs.tl, device=randn.device),
-                 "num_video_frames": vs.tl, "time_context": vs.time_context(c, uc)}
+        frames = vs.frames if vs is not None else slice(0, num_frames)
+        tl = vs.tl if vs is not None else num_frames
+        x = randn[frames].clone()
+        c_l, uc_l = (vs.shard_cond(c), vs.shard_cond(uc)) if vs is not None else (c, uc)
+        nb = 1 if cs is not None else 2
+        extra = {"image_only_indicator": torch.zeros(nb, tl, device=randn.device), "num_video_frames": tl}
+        if vs is not None:
+            tc = vs.time_context(c, uc)                       # [2, 1, ctx] in [uc; c] order
+            extra["time_context"] = tc[cs.rank:cs.rank + 1] if cs is not None else tc
 
         def denoiser(inp, sigma, cond):
             return self.denoiser(self.model, inp, sigma, cond, **extra)
 
         sampler = copy.copy(self.sampler)
-        sampler.guider = vs.shard_guider(self.sampler.guider)
-        unet.view_shard = decoder.view_shard = vs
+        guider = vs.shard_guider(self.sampler.guider) if vs is not None else self.sampler.guider
+        sampler.guider = CfgSplitGuider(guider, cs) if cs is not None else guider
         try:
-            z = sampler(denoiser, x, cond=c_l, uc=uc_l)
-            return self.first_stage_model.decode(1.0 / self.scale_factor * z, timesteps=vs.tl)
+            unet.view_shard = vs
+            z = sampler(denoiser, x, cond=c_l, uc=uc_l)       # this rank's sampling frames, identical across a CFG pair
+            # decode blocks are the sampling blocks or nested inside them
+            off = dvs.t0 - (vs.t0 if vs is not None else 0)
+            assert 0 <= off and off + dvs.tl <= z.shape[0], "decode blocks must lie inside the sampling blocks"
+            decoder.view_shard = dvs
+            return self.first_stage_model.decode(1.0 / self.scale_factor * z[off:off + dvs.tl].contiguous(),
+                                                 timesteps=dvs.tl)
         finally:
             unet.view_shard = decoder.view_shard = None

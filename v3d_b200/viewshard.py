@@ -213,3 +213,116 @@ class ViewShard:
         if hasattr(g, "_scale_dev"):
             g._scale_dev = None
         return g
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CFG-pair split: the second free axis of SURVEY.md 8(e)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class CfgSplit:
+    """The unconditional and the conditional half of the classifier-free-guidance batch (guiders.py:88-101, batch order
+    [uc; c]) on two ranks: rank 0 of the pair evaluates the network on (x, uc), rank 1 on (x, c); one all-gather of the
+    two denoised halves ([T, 4, h, w] fp32 each: 1.2 MB at V3D_512) per network evaluation puts [uc; c] on both ranks,
+    which then apply the guidance and the sampler update redundantly.  25 small exchanges per image instead of the
+    ~2600 of frame-sharding, and exactly the unsplit arithmetic (per-sample operators see the same samples)."""
+
+    rank: int                         # 0 = uc half, 1 = c half
+    group: Optional[object] = None
+    exchanges: int = 0
+
+    @classmethod
+    def create(cls, group=None) -> "CfgSplit":
+        if not dist.is_initialized() or dist.get_world_size(group) != 2:
+            raise RuntimeError("CfgSplit needs a process group of exactly two ranks")
+        return cls(dist.get_rank(group), group)
+
+    def gather_halves(self, mine: torch.Tensor) -> torch.Tensor:
+        """[n, ...] on each rank -> [2n, ...] = [rank 0's; rank 1's] on both."""
+        self.exchanges += 1
+        mine = mine.contiguous()
+        out = mine.new_empty((2 * mine.shape[0],) + tuple(mine.shape[1:]))
+        if mine.is_cuda and dist.get_backend(self.group) == "gloo":      # tests: two processes sharing one GPU
+            h = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(h, mine.cpu(), group=self.group)
+            out.copy_(h)
+        else:
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out
+
+
+class CfgSplitGuider:
+    """Wraps a classifier-free guider so that each rank of a CfgSplit pair feeds the network only its half of
+    `prepare_inputs`' [uc; c] batch and the guidance sees the all-gathered pair."""
+
+    def __init__(self, inner, split: CfgSplit):
+        if not hasattr(inner, "scale"):
+            raise RuntimeError("CfgSplit needs a classifier-free guider ([uc; c] batch); got " + type(inner).__name__)
+        self.inner, self.split = inner, split
+
+    def prepare_inputs(self, x, s, c, uc):
+        x2, s2, c2 = self.inner.prepare_inputs(x, s, c, uc)
+        n, r = x.shape[0], self.split.rank
+        half = slice(r * n, (r + 1) * n)
+        cond = {k: (v[half] if torch.is_tensor(v) and v.ndim > 0 and v.shape[0] == 2 * n else v) for k, v in c2.items()}
+        return x2[half], s2[half], cond
+
+    def __call__(self, x_half, sigma):
+        return self.inner(self.split.gather_halves(x_half), sigma)
+
+
+@dataclass
+class ShardPlan:
+    """How ONE image is spread over the ranks of a job: `sample` = frame blocks of the sampler/UNet (None = all frames),
+    `cfg` = CFG-pair split (None = both halves on every rank), `decode` = frame blocks of the first-stage decode (always
+    set: the decode has no CFG axis, so with a CFG split every pair divides its frames once more).
+
+        views      world = P      sample = decode = P frame blocks
+        cfg        world = 2      sample = None, cfg pair = the two ranks, decode = 2 frame blocks
+        cfg+views  world = 2 P    rank g = 2 v + r: frame block v of P, CFG half r; decode = each block split in two
+    """
+
+    mode: str
+    num_frames: int
+    sample: Optional[ViewShard]
+    cfg: Optional[CfgSplit]
+    decode: ViewShard
+
+    @classmethod
+    def create(cls, num_frames: int, mode: str = "views") -> "ShardPlan":
+        if not dist.is_initialized():
+            raise RuntimeError("ShardPlan.create needs an initialised torch.distributed process group")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if mode == "views":
+            vs = ViewShard.create(num_frames)
+            return cls(mode, num_frames, vs, None, vs)
+        if mode == "cfg":
+            if world != 2:
+                raise RuntimeError("mode 'cfg' runs on exactly 2 ranks (use 'cfg+views' for more)")
+            return cls(mode, num_frames, None, CfgSplit.create(), ViewShard.create(num_frames))
+        if mode == "cfg+views":
+            if world < 4 or world % 2:
+                raise RuntimeError("mode 'cfg+views' needs an even number (>= 4) of ranks")
+            pv = world // 2
+            v, r = divmod(rank, 2)
+            # every rank creates every group, in the same order (torch.distributed requirement)
+            pair_groups = [dist.new_group([2 * i, 2 * i + 1]) for i in range(pv)]
+            view_groups = [dist.new_group([2 * i + j for i in range(pv)]) for j in range(2)]
+            sample = ViewShard(num_frames, v, pv, view_groups[r], partition_frames(num_frames, pv))
+            blocks = []
+            for t0, n in sample.blocks:
+                if n < 2:
+                    raise ValueError(f"{num_frames} frames over {pv} blocks leave a block too small to split for the decode")
+                blocks += [(t0, (n + 1) // 2), (t0 + (n + 1) // 2, n // 2)]
+            return cls(mode, num_frames, sample, CfgSplit(r, pair_groups[v]), ViewShard(num_frames, rank, world, None, blocks))
+        raise ValueError(f"unknown shard mode {mode!r} (views | cfg | cfg+views)")
+
+    def gather_frames(self, local: torch.Tensor) -> torch.Tensor:
+        return self.decode.gather_frames(local)
+
+    def describe(self) -> Dict:
+        return {"mode": self.mode, "sample_blocks": self.sample.blocks if self.sample else None,
+                "cfg_rank": self.cfg.rank if self.cfg else None, "decode_blocks": self.decode.blocks,
+                "exchanges": {**(self.sample.exchanges if self.sample else {}),
+                              "cfg_gather": self.cfg.exchanges if self.cfg else 0,
+                              **{"decode_" + k: v for k, v in self.decode.exchanges.items()
+                                 if self.decode is not self.sample}}}
