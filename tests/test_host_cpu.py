@@ -282,3 +282,30 @@ def test_bench_reference_arm_prints_contract_line():
     assert set(cb["last_sample_raw_s"]) == {"unet_s", "decode_s"} and cb["thread_calibration_s"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
+
+
+def test_orbit_cameras_match_reference_golden(tmp_path):
+    """the frame <-> camera convention of the generated views against the reference's own
+    get_uniform_poses (tests/golden/cameras.npz, made by oracle/make_golden_cameras.py), and the mp4 writer."""
+    import numpy as np
+
+    from v3d_b200 import wire
+
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "cameras.npz")
+    names = [k for k in gold.files if not k.endswith("_args")]
+    assert len(names) == 4
+    for name in names:
+        t, r, e, gl = gold[name + "_args"]
+        mine = wire.orbit_poses(int(t), float(r), float(e), opengl=bool(gl))
+        assert mine.shape == gold[name].shape and mine.dtype == np.float32
+        assert np.abs(mine - gold[name]).max() <= 2e-7, name
+    infos = wire.camera_infos()
+    assert len(infos) == 18 and infos[0]["width"] == 512 and abs(infos[0]["FovX"] - np.deg2rad(60.0)) < 1e-12
+    # frame 0 looks down the -x axis from (2, 0, 0); R T reproduce the world-to-camera transform
+    c2w = wire.orbit_poses()
+    assert np.allclose(c2w[0, :3, 3], [2.0, 0.0, 0.0]) and np.allclose(c2w[0, :3, 2], [-1.0, 0.0, 0.0])
+    w2c = np.linalg.inv(c2w[5])
+    assert np.allclose(infos[5]["R"].T, w2c[:3, :3], atol=1e-6) and np.allclose(infos[5]["T"], w2c[:3, 3], atol=1e-6)
+    frames = (np.random.default_rng(0).random((4, 32, 32, 3)) * 255).astype(np.uint8)
+    path = wire.write_video(str(tmp_path / "v.mp4"), frames, fps=3)
+    assert Path(path).stat().st_size > 0
