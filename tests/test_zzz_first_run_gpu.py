@@ -8,6 +8,7 @@ this list.  The CTA-pair GEMM test is not run from here (a cluster-barrier bug c
 manual `V3D_RUN_UNVALIDATED=1 pytest -k cta_pair` under `timeout`.
 """
 import os
+import signal
 import subprocess
 import sys
 from pathlib import Path
@@ -39,11 +40,17 @@ def test_first_hardware_run(group):
     env = dict(os.environ, V3D_RUN_UNVALIDATED="1")
     selection, limit = GROUPS[group]
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", *selection]
+    # own session: on a timeout the whole process group goes (pytest child and any workers it spawned), so nothing
+    # is left holding the GPU for the steps that follow this suite
+    proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            start_new_session=True)
     try:
-        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=limit)
-        text, rc = res.stdout[-6000:] + res.stderr[-3000:], res.returncode
-    except subprocess.TimeoutExpired as e:
-        text, rc = f"TIMEOUT after {e.timeout}s\n{(e.stdout or b'')[-3000:]!r}", 124
+        out, _ = proc.communicate(timeout=limit)
+        text, rc = out[-8000:], proc.returncode
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, _ = proc.communicate()
+        text, rc = f"TIMEOUT after {limit}s\n{(out or '')[-4000:]}", 124
     try:
         OUT.mkdir(exist_ok=True)
         (OUT / f"first_run_{group}.log").write_text(f"exit {rc}\n{text}")
