@@ -309,3 +309,18 @@ def test_orbit_cameras_match_reference_golden(tmp_path):
     frames = (np.random.default_rng(0).random((4, 32, 32, 3)) * 255).astype(np.uint8)
     path = wire.write_video(str(tmp_path / "v.mp4"), frames, fps=3)
     assert Path(path).stat().st_size > 0
+
+
+def test_guider_attribute_pokes_match_reference_semantics():
+    """app.py:143-145 assigns guider.max_scale / min_scale after construction; like the reference
+    (guiders.py:71-76 computes `scale` once in __init__) that leaves the per-frame scale untouched, while assigning
+    `scale` itself is honoured."""
+    from v3d_b200.sampling import LinearPredictionGuider
+
+    g = LinearPredictionGuider(max_scale=3.5, min_scale=1.5, num_frames=6)
+    before = g.scale.clone()
+    g.max_scale, g.min_scale = 9.0, 9.0
+    assert torch.equal(g.scale, before) and g.scale.shape == (1, 6)
+    assert torch.allclose(before, torch.linspace(1.5, 3.5, 6).unsqueeze(0))
+    g.scale = torch.full((1, 6), 2.0)
+    assert float(g.scale.sum()) == 12.0
