@@ -24,6 +24,7 @@ OUT = TESTS.parent / "gpurun_out"
 # 4-process composite plan and the NCCL variants are run by hand (tools/gpu_round.sh).
 GROUPS = {
     "kernels": ([str(TESTS / "test_kernels_gpu.py"), "-k", "heun_step_kernel or concat_timestep_embedder"], 300),
+    "attention_poly_exp2": ([str(TESTS / "test_kernels_gpu.py"), "-k", "attention_poly_exp2"], 600),
     "parity": ([str(TESTS / "test_parity_gpu.py"), "-k", "encoder or heun or vanilla or central"], 600),
     "viewshard_kernels": ([str(TESTS / "test_viewshard_gpu.py"), "-k", "halo_mode or split_kv"], 300),
     "viewshard_engine": ([str(TESTS / "test_viewshard_gpu.py"), "-k",

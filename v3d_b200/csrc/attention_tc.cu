@@ -14,6 +14,7 @@
 // sum); otherwise P is simply up to 256x larger, which fp32 sums and bf16 P hold without loss.  Mathematically the
 // result is the exact softmax; only rounding differs.
 // TMEM per CTA: 256 columns; shared memory ~97 KB -> two CTAs per SM.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -37,6 +38,30 @@ constexpr int AT_SMEM = AT_OFF_BAR + 256;
 constexpr uint32_t AT_TMEM_COLS = 256;
 constexpr float AT_RESCALE_LOG2 = 8.0f;            // move the softmax reference only for a > 2^8 overshoot
 
+// 2^x for a pair of fp32 values on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic
+// add, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 8.0e-5, a 25th of a bf16 half-ulp), then
+// n is added into the exponent field (the integer sits in the low mantissa bits of the magic sum, so `bits << 23` is
+// n << 23).  x must be >= -126 (callers clamp); large positive x does not occur (lagged reference: x <= 8 + noise).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);
+  const uint64_t x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t t2 = add2(x2, magic);
+  const uint64_t f2 = add2(x2, fma2(t2, pack2(-1.0f, -1.0f), magic));  // x - (t - magic)
+  uint64_t q2 = fma2(f2, pack2(0.05519810691475868f, 0.05519810691475868f),
+                     pack2(0.24267712235450745f, 0.24267712235450745f));
+  q2 = fma2(q2, f2, pack2(0.6932618021965027f, 0.6932618021965027f));
+  q2 = fma2(q2, f2, pack2(0.9999227523803711f, 0.9999227523803711f));
+  float q0, q1, t0, t1;
+  unpack2(q2, q0, q1);
+  unpack2(t2, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// POLY: how many of the 8 key chunks of a tile take their exp2 from exp2_poly2 instead of MUFU ex2.approx
+// (0 = none, the validated kernel; 1 = every 4th chunk, 2 = every 2nd, 3 = three of four).  The softmax is
+// MUFU-bound (16 ex2 / clk / SM against 128 fp32 lanes): moving part of the row to the FMA pipe balances the two.
+template <int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, bf16* __restrict__ O, long long ldo, int ntok,
@@ -223,7 +248,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           const int i = c * 8 + e;
           float x0, x1;
           unpack2(fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sl2, nm2), x0, x1);
-          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          float p0, p1;
+          if (POLY != 0 && (POLY == 1 ? (c & 3) == 3 : (POLY == 2 ? (c & 1) == 1 : (c & 3) != 0))) {
+            exp2_poly2(x0, x1, p0, p1);
+          } else {
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+          }
           if (TAIL) {
             if (kbase + i >= ntok) p0 = 0.f;
             if (kbase + i + 1 >= ntok) p1 = 0.f;
@@ -308,17 +339,27 @@ int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, 
   if ((rc = make_tmap_bf16(&mq, q, 3, dims, str, box_q))) return rc;
   if ((rc = make_tmap_bf16(&mk, k, 3, dims, str, box_kv))) return rc;
   if ((rc = make_tmap_bf16(&mv, v, 3, dims, str, box_kv))) return rc;
-  static bool cfg = false;
-  if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  // V3D_ATTN_POLY = 1 | 2 | 3 (read once per process): opt-in FMA-pipe exp2 for 2 / 4 / 6 of a tile's 8 key chunks;
+  // not yet timed on hardware.  Default 0 = the validated kernel (its SASS is unchanged by the template).
+  static int poly = -1;
+  if (poly < 0) {
+    const char* v = getenv("V3D_ATTN_POLY");
+    poly = v ? atoi(v) : 0;
+    if (poly < 0 || poly > 3) poly = 0;
+  }
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, bf16*, long long, int, float);
+  static const Kern kerns[4] = {attn_tc_kernel<0>, attn_tc_kernel<1>, attn_tc_kernel<2>, attn_tc_kernel<3>};
+  static bool cfg[4] = {false, false, false, false};
+  if (!cfg[poly]) {
+    cudaError_t e = cudaFuncSetAttribute(kerns[poly], cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) {
       set_error("attn_tc smem attr: %s", cudaGetErrorString(e));
       return V3D_ERR_CUDA;
     }
-    cfg = true;
+    cfg[poly] = true;
   }
   dim3 grid((ntok + AT_BM - 1) / AT_BM, nheads, nbatch);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(
+  kerns[poly]<<<grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(
       mq, mk, mv, static_cast<bf16*>(o), ld_o, ntok, scale * 1.44269504088896340736f);
   V3D_CHECK_LAUNCH("attn_tc_kernel");
   return V3D_OK;
