@@ -12,6 +12,7 @@
 #                 with the switch off / on
 #   attn_poly     FMA-pipe exp2 variants of the spatial attention (V3D_ATTN_POLY=1..3): tests, then timings 0..3
 #   bench         bench.py (default N=1) -> gpurun_out/bench.json ; bench.py --impl reference -> bench_ref.json
+#   sweep         BASELINE configs[4]: S in {10,25,50} x T in {14,18,25} on one GPU -> gpurun_out/sweep.json
 #   ncu_launches  the ncu launch list of one EDM step + decode (gpu__time_duration.sum, --clock-control none)
 #   ncu_full      ncu --set full of the named kernels (GEMM conv/geglu/proj, attention, GroupNorm, LayerNorm)
 #   viewshard2    (2 GPUs) NCCL engine parity test, then bench.py --shard views and --shard images at N=2
@@ -49,6 +50,8 @@ for stage in "$@"; do
     bench)
       run 900 bench.json $PY bench.py --steps 3 --warmup 3
       run 900 bench_ref.json $PY bench.py --impl reference --steps 1 --warmup 1 ;;
+    sweep)
+      run 1500 sweep.log $PY tools/sweep.py ;;
     bench_pair)
       V3D_GEMM_2CTA=1 run 900 bench_pair.json $PY bench.py --steps 3 --warmup 3 --no-cpu-baseline ;;
     ncu_launches)
