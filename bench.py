@@ -405,6 +405,7 @@ def run_native(args) -> None:
     records = []      # (flops, e0, e1) for tensor-core GEMM/conv launches
     families = {}     # op name -> list of (e0, e1)
     shapes = {}       # GEMM shape key -> list of (flops, e0, e1)
+    membound = {}     # memory-bound family -> list of (algorithmic bytes, e0, e1)
     host_only = {"launch_count", "pick_block_n", "geglu_perm"}
     saved = {}
 
@@ -427,6 +428,20 @@ def run_native(args) -> None:
                 shapes.setdefault(skey, []).append((2.0 * rows * N * K * taps, e0, e1))
                 fam = "gemm.conv3x3" if kw.get("conv") is not None else ("gemm.temporal" if taps == 3 else "gemm.linear")
             families.setdefault(fam, []).append((e0, e1))
+            try:  # algorithmic HBM bytes of the memory-bound families; never fatal
+                nbytes = None
+                if name == "groupnorm_stats":          # (x, stats, rows_per_sample, nsamples, c): read x once
+                    nbytes = 2 * a[2] * a[3] * a[4]
+                elif name == "groupnorm_apply":        # (x, y, stats, gamma, beta, rows_per_sample, nsamples, c)
+                    nbytes = 2 * 2 * a[5] * a[6] * a[7]
+                elif name == "layernorm":              # (x, y, gamma, beta, rows, c): read + write (+ the fused sum)
+                    nbytes = 2 * (3 if kw.get("ysum") is not None else 2) * a[4] * a[5]
+                elif name == "attention_temporal":     # (qkv, out, nb, t, s, nheads): q, k, v read, o written
+                    nbytes = 2 * 4 * a[2] * a[3] * a[4] * a[5] * 64
+                if nbytes is not None:
+                    membound.setdefault(name, []).append((float(nbytes), e0, e1))
+            except Exception:
+                pass
             return r
         return probed
 
@@ -464,6 +479,15 @@ def run_native(args) -> None:
     breakdown["_probed_step_ms"] = round(probe_ms, 3)
     breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
 
+    peaks_hbm = float(load_peaks()[0].get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
+    hbm_rows = {}
+    for fam, recs in membound.items():
+        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in recs)
+        gb = sum(b for b, _, _ in recs) / 1e9
+        if ms > 0:
+            hbm_rows[fam] = {"launches": len(recs), "ms": round(ms, 3), "algorithmic_gb": round(gb, 2),
+                             "achieved_gbs": round(gb / (ms * 1e-3), 1),
+                             "frac_of_hbm_peak": round(gb / (ms * 1e-3) / peaks_hbm, 3)}
     traffic = None
     tpath = ROOT / "profiles" / "traffic_r1.json"
     if tpath.exists():
@@ -498,6 +522,9 @@ def run_native(args) -> None:
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
             "breakdown_ms_per_step": breakdown,
             "gemm_shapes_top": shape_rows[:30],
+            "hbm_bound_families": dict(hbm_rows, peak_gbs=peaks_hbm,
+                                       note="algorithmic bytes (each tensor read / written once) over summed CUDA-event "
+                                            "durations of one eager step; many of these tensors fit the 126 MB L2"),
             "model": {"reference_accounting_tflop_per_step": model_tf,
                       "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
         },
