@@ -699,11 +699,12 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   return V3D_OK;
 }
 
-// CTA-pair variants exist for the wide bf16-output tiles only (the shapes that are ingest-bound with one CTA)
+// CTA-pair variants exist for the wide bf16-output tiles only (the shapes that are ingest- or shared-memory-bound
+// with one CTA: 160-wide UNet layers, the 128-wide decoder levels)
 template <int BN, bool CONV>
 static int dispatch_epi_pair(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
                              const GemmEpi& epi, cudaStream_t st) {
-  if constexpr (BN == 160 || BN == 256) {
+  if constexpr (BN == 128 || BN == 160 || BN == 256) {
     switch (epi_kind) {
       case EPI_BF16: return launch<BN, CONV, EPI_BF16, 2>(ma, mb, md, epi, st);
       case EPI_BF16R2: return launch<BN, CONV, EPI_BF16R2, 2>(ma, mb, md, epi, st);
@@ -741,6 +742,7 @@ static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtens
     switch (bn) {
       case 256: return dispatch_epi_pair<256, CONV>(epi_kind, ma, mb, md, epi, st);
       case 160: return dispatch_epi_pair<160, CONV>(epi_kind, ma, mb, md, epi, st);
+      case 128: return dispatch_epi_pair<128, CONV>(epi_kind, ma, mb, md, epi, st);
       default: set_error("no CTA-pair variant for block_n %d", bn); return V3D_ERR_BAD_ARG;
     }
   }
@@ -988,7 +990,7 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     }
     const bool staged_out = !a->out_transposed && !a->out_fp32;
     pair = want_pair == 1 && staged_out && e.num_m_tiles >= 2 &&
-           (bn == 256 || (bn == 160 && a->act != V3D_ACT_GEGLU));
+           (bn == 256 || ((bn == 160 || bn == 128) && a->act != V3D_ACT_GEGLU));  // 128: the decoder's top levels
   }
   {
     const uint64_t ktot = (uint64_t)ntaps * a->K;
