@@ -278,6 +278,77 @@ def workload_config(args, where: str) -> dict:
             "cuda_graph": os.environ.get("V3D_CUDA_GRAPH", "1") != "0"}
 
 
+def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d2h_bytes, sharded, probe_ms,
+                  gemm_records, families, shapes, membound) -> dict:
+    """The JSON line of the native arm from plain numbers (seconds / milliseconds / bytes / FLOPs).
+    gemm_records: [(flops, ms)] of every tensor-core GEMM/conv launch of one probed step; families: {op: [ms]};
+    shapes: {shape key: [(flops, ms)]}; membound: {family: [(algorithmic bytes, ms)]}."""
+    T, S, L = args.frames, args.edm_steps, args.latent
+    gemm_flops = sum(f for f, _ in gemm_records)
+    gemm_ms = sum(m for _, m in gemm_records)
+    breakdown = {k: {"ms": round(sum(v), 3), "launches": len(v)} for k, v in sorted(families.items())}
+    shape_rows = []
+    for k, v in shapes.items():
+        sms = sum(m for _, m in v)
+        fl = sum(f for f, _ in v)
+        shape_rows.append({"shape": k, "launches": len(v), "ms": round(sms, 3),
+                           "tflops": round(fl / sms / 1e9, 1) if sms > 0 else None})
+    shape_rows.sort(key=lambda r: -r["ms"])
+    breakdown["_probed_step_ms"] = round(probe_ms, 3)
+    breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
+
+    peaks, peak_src = load_peaks()
+    peaks_hbm = float(peaks.get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
+    hbm_rows = {}
+    for fam, recs in membound.items():
+        fms = sum(m for _, m in recs)
+        gb = sum(b for b, _ in recs) / 1e9
+        if fms > 0:
+            hbm_rows[fam] = {"launches": len(recs), "ms": round(fms, 3), "algorithmic_gb": round(gb, 2),
+                             "achieved_gbs": round(gb / (fms * 1e-3), 1),
+                             "frac_of_hbm_peak": round(gb / (fms * 1e-3) / peaks_hbm, 3)}
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic_r1.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text())
+        except Exception:
+            traffic = None
+    peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
+    n_img = 1 if sharded else world
+    value = n_img * T * args.steps / secs
+    e2e_value = n_img * T * args.steps / secs_e2e
+    model_tf = work_tf(T, S, L)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    return {
+        "metric": "view-frames/sec", "value": value, "unit": "view-frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": workload_config(args, "gpu"),
+        "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": d2h_bytes * n_img, "ms_per_step": 1000.0 * secs_e2e / args.steps,
+                "api": "DiffusionEngine.sample_views + frames_nchw_to_u8 (+ NCCL frame gather when N > 1)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / temporal conv / implicit 3x3 conv)",
+            "achieved": achieved, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved is not None else None,
+            "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
+            "launches_per_step": len(gemm_records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
+            "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
+            "breakdown_ms_per_step": breakdown,
+            "gemm_shapes_top": shape_rows[:30],
+            "hbm_bound_families": dict(hbm_rows, peak_gbs=peaks_hbm,
+                                       note="algorithmic bytes (each tensor read / written once) over summed CUDA-event "
+                                            "durations of one eager step; many of these tensors fit the 126 MB L2"),
+            "model": {"reference_accounting_tflop_per_step": model_tf,
+                      "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
+        },
+    }
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -464,71 +535,15 @@ def run_native(args) -> None:
         unet.cuda_graphs = graphs_were
         for name, fn in saved.items():
             setattr(ops, name, fn)
-    gemm_flops = sum(r[0] for r in records)
-    gemm_ms = sum(r[1].elapsed_time(r[2]) for r in records)
-    probe_ms = pe0.elapsed_time(pe1)
-    breakdown = {k: {"ms": round(sum(a.elapsed_time(b) for a, b in v), 3), "launches": len(v)}
-                 for k, v in sorted(families.items())}
-    shape_rows = []
-    for k, v in shapes.items():
-        ms = sum(a.elapsed_time(b) for _, a, b in v)
-        fl = sum(f for f, _, _ in v)
-        shape_rows.append({"shape": k, "launches": len(v), "ms": round(ms, 3),
-                           "tflops": round(fl / ms / 1e9, 1) if ms > 0 else None})
-    shape_rows.sort(key=lambda r: -r["ms"])
-    breakdown["_probed_step_ms"] = round(probe_ms, 3)
-    breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
-
-    peaks_hbm = float(load_peaks()[0].get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
-    hbm_rows = {}
-    for fam, recs in membound.items():
-        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in recs)
-        gb = sum(b for b, _, _ in recs) / 1e9
-        if ms > 0:
-            hbm_rows[fam] = {"launches": len(recs), "ms": round(ms, 3), "algorithmic_gb": round(gb, 2),
-                             "achieved_gbs": round(gb / (ms * 1e-3), 1),
-                             "frac_of_hbm_peak": round(gb / (ms * 1e-3) / peaks_hbm, 3)}
-    traffic = None
-    tpath = ROOT / "profiles" / "traffic_r1.json"
-    if tpath.exists():
-        try:
-            traffic = json.loads(tpath.read_text())
-        except Exception:
-            traffic = None
-    peaks, peak_src = load_peaks()
-    peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
-    n_img = 1 if plan is not None else world
-    value = n_img * T * args.steps / secs
-    e2e_value = n_img * T * args.steps / secs_e2e
-    model_tf = work_tf(T, S, L)
-
-    line = {
-        "metric": "view-frames/sec", "value": value, "unit": "view-frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": "strong" if plan is not None else "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": workload_config(args, "gpu"),
-        "e2e": {"value": e2e_value, "unit": "view-frames/s", "h2d_bytes_per_step": h2d_bytes * world,
-                "d2h_bytes_per_step": d2h_bytes * n_img, "ms_per_step": 1000.0 * secs_e2e / args.steps,
-                "api": "DiffusionEngine.sample_views + frames_nchw_to_u8 (+ NCCL frame gather when N > 1)"},
-        "gpu_launches": launches,
-        "clocks": clk,
-        "roofline": {
-            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / temporal conv / implicit 3x3 conv)",
-            "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": (gemm_flops / (gemm_ms * 1e-3) / 1e12) / peak_tf if gemm_ms > 0 else None,
-            "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
-            "launches_per_step": len(records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
-            "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
-            "breakdown_ms_per_step": breakdown,
-            "gemm_shapes_top": shape_rows[:30],
-            "hbm_bound_families": dict(hbm_rows, peak_gbs=peaks_hbm,
-                                       note="algorithmic bytes (each tensor read / written once) over summed CUDA-event "
-                                            "durations of one eager step; many of these tensors fit the 126 MB L2"),
-            "model": {"reference_accounting_tflop_per_step": model_tf,
-                      "achieved_tflops": model_tf / (secs / args.steps), "frac": model_tf / (secs / args.steps) / peak_tf},
-        },
-    }
+    # CUDA events -> plain milliseconds; everything below is host arithmetic (assemble_line, unit-tested on CPU)
+    ms = lambda e0, e1: e0.elapsed_time(e1)
+    line = assemble_line(
+        args, world=world, secs=secs, secs_e2e=secs_e2e, launches=launches, clocks=clk, h2d_bytes=h2d_bytes,
+        d2h_bytes=d2h_bytes, sharded=plan is not None, probe_ms=ms(pe0, pe1),
+        gemm_records=[(f, ms(a, b)) for f, a, b in records],
+        families={k: [ms(a, b) for a, b in v] for k, v in families.items()},
+        shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in shapes.items()},
+        membound={k: [(nb, ms(a, b)) for nb, a, b in v] for k, v in membound.items()})
     if plan is not None:
         line["shard_plan"] = dict(plan.describe(),
                                   cuda_graph_with_collectives=os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1")

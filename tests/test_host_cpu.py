@@ -324,3 +324,41 @@ def test_guider_attribute_pokes_match_reference_semantics():
     assert torch.allclose(before, torch.linspace(1.5, 3.5, 6).unsqueeze(0))
     g.scale = torch.full((1, 6), 2.0)
     assert float(g.scale.sum()) == 12.0
+
+
+def test_bench_native_line_assembly():
+    """bench.py's native-arm JSON line is assembled by a pure function from plain timings: contract keys, the metric
+    arithmetic (whole-job frames / max-over-ranks seconds), roofline fractions and JSON-serialisability, for the
+    default image-parallel run and for a one-image-over-ranks plan."""
+    import argparse
+    import json
+
+    import bench
+
+    args = argparse.Namespace(frames=18, edm_steps=25, latent=64, steps=3, warmup=3, gpus=2, min_cfg=3.5, max_cfg=3.5,
+                              shard="images")
+    kw = dict(world=2, secs=4.5, secs_e2e=4.6, launches=111852, clocks={"sm_mhz": 1700.0, "sm_max_mhz": 1965.0,
+                                                                        "reasons": ["sw_power_cap"], "samples": 20},
+              h2d_bytes=3796992, d2h_bytes=14155776, probe_ms=1500.0,
+              gemm_records=[(2.0e12, 2.0), (1.0e12, 1.0)],
+              families={"gemm.linear": [2.0], "gemm.conv3x3": [1.0], "layernorm": [0.5, 0.5]},
+              shapes={"linear M=8 K=64 N=64": [(2.0e12, 2.0)], "conv3x3 M=8 K=64 N=64": [(1.0e12, 1.0)]},
+              membound={"layernorm": [(3.0e9, 0.5), (3.0e9, 0.5)]})
+    line = bench.assemble_line(args, sharded=False, **kw)
+    json.loads(json.dumps(line))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert line["value"] == pytest.approx(2 * 18 * 3 / 4.5) and line["e2e"]["value"] == pytest.approx(2 * 18 * 3 / 4.6)
+    assert line["scaling"] == "weak" and line["n_gpus"] == 2 and line["ms_per_step"] == pytest.approx(1500.0)
+    assert line["e2e"]["h2d_bytes_per_step"] == 2 * 3796992 and line["e2e"]["d2h_bytes_per_step"] == 2 * 14155776
+    roof = line["roofline"]
+    assert roof["achieved"] == pytest.approx(1000.0) and roof["frac"] == pytest.approx(1000.0 / roof["peak"])
+    assert roof["launches_per_step"] == 2 and roof["gemm_shapes_top"][0]["shape"].startswith("linear")
+    assert roof["hbm_bound_families"]["layernorm"]["achieved_gbs"] == pytest.approx(6000.0)
+    assert roof["model"]["reference_accounting_tflop_per_step"] == pytest.approx(25 * 45.677 + 54.771)
+    assert "image-dp2" in line["config"]["parallelism"] and line["config"]["workload"].startswith("V3D_512")
+    args.shard = "cfg"
+    one = bench.assemble_line(args, sharded=True, **kw)
+    assert one["scaling"] == "strong" and one["value"] == pytest.approx(18 * 3 / 4.5)
+    assert one["e2e"]["d2h_bytes_per_step"] == 14155776 and "plan 'cfg'" in one["config"]["parallelism"]
