@@ -279,7 +279,7 @@ def workload_config(args, where: str) -> dict:
 
 
 def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d2h_bytes, sharded, probe_ms,
-                  gemm_records, families, shapes, membound) -> dict:
+                  gemm_records, families, shapes, membound, decode_families=None) -> dict:
     """The JSON line of the native arm from plain numbers (seconds / milliseconds / bytes / FLOPs).
     gemm_records: [(flops, ms)] of every tensor-core GEMM/conv launch of one probed step; families: {op: [ms]};
     shapes: {shape key: [(flops, ms)]}; membound: {family: [(algorithmic bytes, ms)]}."""
@@ -294,6 +294,8 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
         shape_rows.append({"shape": k, "launches": len(v), "ms": round(sms, 3),
                            "tflops": round(fl / sms / 1e9, 1) if sms > 0 else None})
     shape_rows.sort(key=lambda r: -r["ms"])
+    decode_breakdown = {k: {"ms": round(sum(v), 3), "launches": len(v)} for k, v in sorted((decode_families or {}).items())}
+    decode_breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for v in decode_breakdown.values()), 3)
     breakdown["_probed_step_ms"] = round(probe_ms, 3)
     breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for k, v in breakdown.items() if isinstance(v, dict)), 3)
 
@@ -339,6 +341,7 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
             "launches_per_step": len(gemm_records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
             "breakdown_ms_per_step": breakdown,
+            "breakdown_decode_only_ms": decode_breakdown,   # the first-stage decode's share of the families above
             "gemm_shapes_top": shape_rows[:30],
             "hbm_bound_families": dict(hbm_rows, peak_gbs=peaks_hbm,
                                        note="algorithmic bytes (each tensor read / written once) over summed CUDA-event "
@@ -477,6 +480,8 @@ def run_native(args) -> None:
     families = {}     # op name -> list of (e0, e1)
     shapes = {}       # GEMM shape key -> list of (flops, e0, e1)
     membound = {}     # memory-bound family -> list of (algorithmic bytes, e0, e1)
+    decode_families = {}   # the same per-family events, first-stage decode only
+    phase = {"name": "sample"}
     host_only = {"launch_count", "pick_block_n", "geglu_perm"}
     saved = {}
 
@@ -499,6 +504,8 @@ def run_native(args) -> None:
                 shapes.setdefault(skey, []).append((2.0 * rows * N * K * taps, e0, e1))
                 fam = "gemm.conv3x3" if kw.get("conv") is not None else ("gemm.temporal" if taps == 3 else "gemm.linear")
             families.setdefault(fam, []).append((e0, e1))
+            if phase["name"] == "decode":
+                decode_families.setdefault(fam, []).append((e0, e1))
             try:  # algorithmic HBM bytes of the memory-bound families; never fatal
                 nbytes = None
                 if name == "groupnorm_stats":          # (x, stats, rows_per_sample, nsamples, c): read x once
@@ -524,6 +531,17 @@ def run_native(args) -> None:
     unet = eng.model.diffusion_model
     graphs_were = unet.cuda_graphs
     unet.cuda_graphs = False  # the probe needs eager launches (events between individual kernels)
+    first_stage = eng.first_stage_model
+    decode_method = first_stage.decode
+
+    def decode_tagged(*a, **kw):   # launches made inside the first-stage decode are also booked under "decode"
+        phase["name"] = "decode"
+        try:
+            return decode_method(*a, **kw)
+        finally:
+            phase["name"] = "sample"
+
+    first_stage.decode = decode_tagged
     try:
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -533,6 +551,7 @@ def run_native(args) -> None:
         torch.cuda.synchronize()
     finally:
         unet.cuda_graphs = graphs_were
+        del first_stage.decode          # back to the class's method
         for name, fn in saved.items():
             setattr(ops, name, fn)
     # CUDA events -> plain milliseconds; everything below is host arithmetic (assemble_line, unit-tested on CPU)
@@ -543,7 +562,8 @@ def run_native(args) -> None:
         gemm_records=[(f, ms(a, b)) for f, a, b in records],
         families={k: [ms(a, b) for a, b in v] for k, v in families.items()},
         shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in shapes.items()},
-        membound={k: [(nb, ms(a, b)) for nb, a, b in v] for k, v in membound.items()})
+        membound={k: [(nb, ms(a, b)) for nb, a, b in v] for k, v in membound.items()},
+        decode_families={k: [ms(a, b) for a, b in v] for k, v in decode_families.items()})
     if plan is not None:
         line["shard_plan"] = dict(plan.describe(),
                                   cuda_graph_with_collectives=os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1")

@@ -343,7 +343,7 @@ def test_bench_native_line_assembly():
               gemm_records=[(2.0e12, 2.0), (1.0e12, 1.0)],
               families={"gemm.linear": [2.0], "gemm.conv3x3": [1.0], "layernorm": [0.5, 0.5]},
               shapes={"linear M=8 K=64 N=64": [(2.0e12, 2.0)], "conv3x3 M=8 K=64 N=64": [(1.0e12, 1.0)]},
-              membound={"layernorm": [(3.0e9, 0.5), (3.0e9, 0.5)]})
+              membound={"layernorm": [(3.0e9, 0.5), (3.0e9, 0.5)]}, decode_families={"gemm.conv3x3": [1.0]})
     line = bench.assemble_line(args, sharded=False, **kw)
     json.loads(json.dumps(line))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -356,6 +356,7 @@ def test_bench_native_line_assembly():
     assert roof["achieved"] == pytest.approx(1000.0) and roof["frac"] == pytest.approx(1000.0 / roof["peak"])
     assert roof["launches_per_step"] == 2 and roof["gemm_shapes_top"][0]["shape"].startswith("linear")
     assert roof["hbm_bound_families"]["layernorm"]["achieved_gbs"] == pytest.approx(6000.0)
+    assert roof["breakdown_decode_only_ms"] == {"gemm.conv3x3": {"ms": 1.0, "launches": 1}, "_sum_of_kernels_ms": 1.0}
     assert roof["model"]["reference_accounting_tflop_per_step"] == pytest.approx(25 * 45.677 + 54.771)
     assert "image-dp2" in line["config"]["parallelism"] and line["config"]["workload"].startswith("V3D_512")
     args.shard = "cfg"
