@@ -279,7 +279,7 @@ def workload_config(args, where: str) -> dict:
 
 
 def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d2h_bytes, sharded, probe_ms,
-                  gemm_records, families, shapes, membound, decode_families=None) -> dict:
+                  gemm_records, families, shapes, membound, decode_families=None, decode_shapes=None) -> dict:
     """The JSON line of the native arm from plain numbers (seconds / milliseconds / bytes / FLOPs).
     gemm_records: [(flops, ms)] of every tensor-core GEMM/conv launch of one probed step; families: {op: [ms]};
     shapes: {shape key: [(flops, ms)]}; membound: {family: [(algorithmic bytes, ms)]}."""
@@ -287,13 +287,17 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
     gemm_flops = sum(f for f, _ in gemm_records)
     gemm_ms = sum(m for _, m in gemm_records)
     breakdown = {k: {"ms": round(sum(v), 3), "launches": len(v)} for k, v in sorted(families.items())}
-    shape_rows = []
-    for k, v in shapes.items():
-        sms = sum(m for _, m in v)
-        fl = sum(f for f, _ in v)
-        shape_rows.append({"shape": k, "launches": len(v), "ms": round(sms, 3),
-                           "tflops": round(fl / sms / 1e9, 1) if sms > 0 else None})
-    shape_rows.sort(key=lambda r: -r["ms"])
+    def shape_table(table):
+        out = []
+        for k, v in (table or {}).items():
+            sms = sum(m for _, m in v)
+            fl = sum(f for f, _ in v)
+            out.append({"shape": k, "launches": len(v), "ms": round(sms, 3),
+                        "tflops": round(fl / sms / 1e9, 1) if sms > 0 else None})
+        out.sort(key=lambda r: -r["ms"])
+        return out
+
+    shape_rows = shape_table(shapes)
     decode_breakdown = {k: {"ms": round(sum(v), 3), "launches": len(v)} for k, v in sorted((decode_families or {}).items())}
     decode_breakdown["_sum_of_kernels_ms"] = round(sum(v["ms"] for v in decode_breakdown.values()), 3)
     breakdown["_probed_step_ms"] = round(probe_ms, 3)
@@ -343,6 +347,7 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
             "breakdown_ms_per_step": breakdown,
             "breakdown_decode_only_ms": decode_breakdown,   # the first-stage decode's share of the families above
             "gemm_shapes_top": shape_rows[:30],
+            "gemm_shapes_decode": shape_table(decode_shapes)[:20],
             "hbm_bound_families": dict(hbm_rows, peak_gbs=peaks_hbm,
                                        note="algorithmic bytes (each tensor read / written once) over summed CUDA-event "
                                             "durations of one eager step; many of these tensors fit the 126 MB L2"),
@@ -481,6 +486,7 @@ def run_native(args) -> None:
     shapes = {}       # GEMM shape key -> list of (flops, e0, e1)
     membound = {}     # memory-bound family -> list of (algorithmic bytes, e0, e1)
     decode_families = {}   # the same per-family events, first-stage decode only
+    decode_shapes = {}     # GEMM shapes of the decode
     phase = {"name": "sample"}
     host_only = {"launch_count", "pick_block_n", "geglu_perm"}
     saved = {}
@@ -502,6 +508,8 @@ def run_native(args) -> None:
                     " geglu" if kw.get("act", 0) == ops.ACT_GEGLU else "", " +R1" if kw.get("r1") is not None else "",
                     " +R2" if kw.get("r2") is not None else "", " f32" if kw.get("out_fp32") else "")
                 shapes.setdefault(skey, []).append((2.0 * rows * N * K * taps, e0, e1))
+                if phase["name"] == "decode":
+                    decode_shapes.setdefault(skey, []).append((2.0 * rows * N * K * taps, e0, e1))
                 fam = "gemm.conv3x3" if kw.get("conv") is not None else ("gemm.temporal" if taps == 3 else "gemm.linear")
             families.setdefault(fam, []).append((e0, e1))
             if phase["name"] == "decode":
@@ -563,7 +571,8 @@ def run_native(args) -> None:
         families={k: [ms(a, b) for a, b in v] for k, v in families.items()},
         shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in shapes.items()},
         membound={k: [(nb, ms(a, b)) for nb, a, b in v] for k, v in membound.items()},
-        decode_families={k: [ms(a, b) for a, b in v] for k, v in decode_families.items()})
+        decode_families={k: [ms(a, b) for a, b in v] for k, v in decode_families.items()},
+        decode_shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in decode_shapes.items()})
     if plan is not None:
         line["shard_plan"] = dict(plan.describe(),
                                   cuda_graph_with_collectives=os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1")
