@@ -413,7 +413,7 @@ def test_single_rank_view_shard_schedule_equals_unsharded():
     assert vs.exchanges["halo"] == 2 * 44 + 29 and vs.exchanges["kv_allgather"] == 32
 
 
-def _plan_worker(rank: int, world: int, port: int, T: int, mode: str, q):
+def _plan_worker(rank: int, world: int, port: int, T: int, mode: str, q, sampler: str = "euler"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, str(Path(ROOT) / "tests"))
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
@@ -428,7 +428,7 @@ def _plan_worker(rank: int, world: int, port: int, T: int, mode: str, q):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     plan = ShardPlan.create(T, mode)
-    eng, _, _ = cpu_shims.cpu_engine(T, 2)
+    eng, _, _ = cpu_shims.cpu_engine(T, 2, sampler_cls=cpu_shims.CpuHeun if sampler == "heun" else cpu_shims.CpuEuler)
     x, c, uc = synth.synth_inputs(T, 8)
     g = torch.Generator().manual_seed(5)
     c = dict(c, crossattn=c["crossattn"] + 0.5 * torch.randn(T, 1, 1024, generator=g))
@@ -436,7 +436,7 @@ def _plan_worker(rank: int, world: int, port: int, T: int, mode: str, q):
         ref = eng.sample_views(x.clone(), c, uc, num_frames=T)
         mine = eng.sample_views(x.clone(), c, uc, num_frames=T, shard=plan)
         gathered = plan.gather_frames(mine)
-    q.put({"rank": rank, "decode_block": (plan.decode.t0, plan.decode.tl),
+    q.put({"rank": rank, "decode_block": (plan.decode.t0, plan.decode.tl), "finite": bool(torch.isfinite(mine).all()),
            "local_rel": _rel(mine, ref[plan.decode.frames]), "gathered_rel": _rel(gathered, ref),
            "plan": plan.describe()})
     dist.barrier()
@@ -464,3 +464,19 @@ def test_cfg_split_plans_match_unsharded_gloo(mode, world, T):
     else:
         assert [r["plan"]["sample_blocks"] for r in res] == [[(0, 3), (3, 2)]] * 4
         assert [r["decode_block"] for r in res] == [(0, 2), (2, 1), (3, 1), (4, 1)]
+
+
+def _plan_worker_heun(rank, world, port, T, mode, q):
+    _plan_worker(rank, world, port, T, mode, q, sampler="heun")
+
+
+def test_cfg_split_with_heun_sampler_matches_unsharded_gloo():
+    """HeunEDMSampler evaluates the network twice per step (once on the last, first-order step): the CFG-pair split
+    gathers the halves after every evaluation - 3 gathers for 2 steps - and still reproduces the unsharded result."""
+    from mp_util import run_workers
+
+    res = sorted(run_workers(_plan_worker_heun, 2, (4, "cfg"), timeout=900), key=lambda r: r["rank"])
+    print(res)
+    for r in res:
+        assert r["finite"] and r["local_rel"] <= 1e-6 and r["gathered_rel"] <= 1e-6, r
+        assert r["plan"]["exchanges"]["cfg_gather"] == 3
