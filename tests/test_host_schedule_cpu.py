@@ -480,3 +480,29 @@ def test_cfg_split_with_heun_sampler_matches_unsharded_gloo():
     for r in res:
         assert r["finite"] and r["local_rel"] <= 1e-6 and r["gathered_rel"] <= 1e-6, r
         assert r["plan"]["exchanges"]["cfg_gather"] == 3
+
+
+@pytest.mark.parametrize("tag", ["encoder_small", "encoder_full"])
+def test_encoder_host_schedule_matches_reference_golden(tag):
+    """The native Encoder's schedule + DiagonalGaussianRegularizer against the REAL reference's moments and sampled
+    latent (tests/golden/encoder_*.pt), with the noise the reference drew."""
+    import json
+
+    import emu_ops
+    from oracle import ref_encoder, synth
+    from v3d_b200.encoder import DiagonalGaussianRegularizer, Encoder
+
+    gold_dir = Path(ROOT) / "tests" / "golden"
+    m = json.loads((gold_dir / "MANIFEST.json").read_text())[tag]
+    gold = torch.load(gold_dir / f"{tag}.pt")
+    enc = Encoder(attn_type="vanilla", double_z=True, z_channels=4, resolution=m["image_hw"], in_channels=3, out_ch=3,
+                  ch=m["ch"], ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    sd = synth.synth_state_dict(ref_encoder.encoder_param_shapes(ref_encoder.EncoderSpec(ch=m["ch"])),
+                                seed=m["weight_seed"])
+    enc.load_state_dict(sd)
+    with emu_ops.patched(), torch.no_grad():
+        mom = enc.eval()._run(enc._pack(torch.device("cpu")), gold["x"])
+    z, _ = DiagonalGaussianRegularizer()(mom, noise=gold["noise"])
+    r, rz = _rel(mom, gold["moments"]), _rel(z, gold["z"])
+    print(tag, "moments rel-L2", r, "z rel-L2", rz)
+    assert r <= 3e-2 and rz <= 3e-2
