@@ -506,3 +506,59 @@ def test_encoder_host_schedule_matches_reference_golden(tag):
     r, rz = _rel(mom, gold["moments"]), _rel(z, gold["z"])
     print(tag, "moments rel-L2", r, "z rel-L2", rz)
     assert r <= 3e-2 and rz <= 3e-2
+
+
+@pytest.mark.parametrize("tag", ["unet_small", "unet_small_t18", "unet_full"])
+def test_unet_host_schedule_matches_reference_golden_with_block_taps(tag):
+    """The CPU twin of tests/test_parity_gpu.py::test_unet_forward_matches_reference: output AND per-block taps of the
+    UNet schedule against the REAL reference's golden outputs (same bounds: taps 2e-2, output 3e-2 / cosine 0.999)."""
+    import json
+
+    import emu_ops
+    from oracle import synth
+    from v3d_b200.unet import VideoUNet
+
+    gold_dir = Path(ROOT) / "tests" / "golden"
+    m = json.loads((gold_dir / "MANIFEST.json").read_text())[tag]
+    gold = torch.load(gold_dir / f"{tag}.pt")
+    net = VideoUNet(**dict(UNET_KW, model_channels=m["model_channels"]))
+    net.load_state_dict(synth.synth_state_dict(net.param_shapes(), seed=m["weight_seed"]), strict=True)
+    T, hw = m["T"], m["latent_hw"]
+    x, c, uc = synth.synth_inputs(T, hw)
+    xin = torch.cat([torch.cat([x, x]), torch.cat([uc["concat"], c["concat"]])], 1)
+    ctx = torch.cat([uc["crossattn"], c["crossattn"]])
+    y = torch.cat([uc["vector"], c["vector"]])
+    taps = {k[4:]: None for k in gold if k.startswith("tap:")}
+    net.debug_taps = taps
+    with emu_ops.patched():
+        out = _run_unet(net.eval(), net._pack(torch.device("cpu")), xin, gold["timesteps"], ctx.reshape(2 * T, -1), y, T)
+    report = [(name, _rel(val[[0, T]][:, ::8], gold["tap:" + name])) for name, val in taps.items()]
+    r, cs = _rel(out, gold["out"]), _cos(out, gold["out"])
+    print(tag, "rel-L2", r, "cos", cs, "worst tap", max(report, key=lambda t: t[1]))
+    assert all(v is not None for v in taps.values()) and len(report) >= 4
+    assert all(e <= 2e-2 for _, e in report), report
+    assert r <= 3e-2 and cs >= 0.999
+
+
+@pytest.mark.parametrize("tag", ["decoder_small", "decoder_small_2videos", "decoder_full"])
+def test_decoder_host_schedule_matches_reference_golden(tag):
+    """Decoder schedule vs the REAL reference's decode; `decoder_small_2videos` decodes two videos in one batch
+    (nb = 2: the 3-D norms and temporal convs must not couple them)."""
+    import json
+
+    import emu_ops
+    from oracle import synth
+    from v3d_b200.decoder import VideoDecoder
+
+    gold_dir = Path(ROOT) / "tests" / "golden"
+    m = json.loads((gold_dir / "MANIFEST.json").read_text())[tag]
+    gold = torch.load(gold_dir / f"{tag}.pt")
+    dec = VideoDecoder(**dict(DEC_KW, ch=m["ch"]))
+    dec.load_state_dict(synth.synth_state_dict(dec.param_shapes(), seed=m["weight_seed"]), strict=True)
+    z = gold["z"] / 0.18215
+    B, T = z.shape[0], m["T"]
+    with emu_ops.patched(), torch.no_grad():
+        out = dec.eval()._run(dec._pack(torch.device("cpu")), z, B, T, B // T, z.shape[2], z.shape[3])
+    r, cs = _rel(out, gold["out"]), _cos(out, gold["out"])
+    print(tag, "rel-L2", r, "cos", cs)
+    assert out.shape == gold["out"].shape and r <= 3e-2 and cs >= 0.999
