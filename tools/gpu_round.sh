@@ -41,6 +41,10 @@ for stage in "$@"; do
       run 900 first_fullsize.log $PY -m pytest tests/test_fullsize_gpu.py -m gpu -q -s
       unset V3D_RUN_UNVALIDATED ;;
     pair)
+      # the staged bring-up probe first: bounded waits, names the primitive that misbehaves instead of hanging
+      [ -x tools/ubench/pair_min ] || nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr \
+        -I include -I v3d_b200/csrc -o tools/ubench/pair_min tools/ubench/pair_min.cu v3d_b200/csrc/host_util.cu
+      run 60 pair_probe.log tools/ubench/pair_min
       V3D_RUN_UNVALIDATED=1 run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
       run 300 micro_single.log $PY tools/microbench.py gemm conv
       V3D_GEMM_2CTA=1 run 300 micro_pair.log $PY tools/microbench.py gemm conv ;;
