@@ -562,3 +562,35 @@ def test_decoder_host_schedule_matches_reference_golden(tag):
     r, cs = _rel(out, gold["out"]), _cos(out, gold["out"])
     print(tag, "rel-L2", r, "cos", cs)
     assert out.shape == gold["out"].shape and r <= 3e-2 and cs >= 0.999
+
+
+@pytest.mark.parametrize("T,hw", [(1, 8), (2, 24), (3, 40)])
+def test_unet_host_schedule_edge_geometries_match_oracle(T, hw):
+    """Edge cases of the schedule against the oracle: a single frame (temporal attention / (3,1,1) convs / 3-D norms
+    over T = 1), and latents that do not tile into power-of-two boxes (24 -> 12 -> 6 -> 3 and 40 -> 20 -> 10 -> 5: every
+    3x3 convolution then takes the explicit im2row path instead of the TMA gather)."""
+    import emu_ops
+    from oracle import ref_unet
+    from v3d_b200.unet import conv_tiles_ok
+
+    net, sd = _build_unet()
+    xin, ts, ctx, y = _unet_inputs(T, hw)
+    with emu_ops.patched():
+        out = _run_unet(net, net._pack(torch.device("cpu")), xin, ts, ctx.reshape(2 * T, -1), y, T)
+    with torch.no_grad():
+        ref = ref_unet.unet_forward(sd, ref_unet.UNetSpec(model_channels=64), xin, ts, ctx, y, T, torch.zeros(2, T))
+    r, cs = _rel(out, ref), _cos(out, ref)
+    print((T, hw), "rel-L2", r, "cos", cs, "tma-gather geometry:", conv_tiles_ok(hw, hw))
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert r <= 3e-2 and cs >= 0.999, (r, cs)
+    if hw in (24, 40):
+        assert not conv_tiles_ok(hw, hw)
+
+
+def test_unet_rejects_latents_whose_skips_would_not_line_up():
+    """12 -> 6 -> 3 -> 2 -> (x2) 4 != 3: the reference dies in th.cat (video_model.py:483); the drop-in raises before
+    launching anything (the kernels take raw pointers: a mismatched skip would be an out-of-bounds read)."""
+    net, _ = _build_unet()
+    xin, ts, ctx, y = _unet_inputs(2, 12)
+    with pytest.raises(RuntimeError, match="divisible by 8"):
+        net._prepare(xin, ts, ctx, y, None, 2, torch.zeros(2, 2))

@@ -665,6 +665,11 @@ class VideoUNet(KernelModule):
         B, cin, H, W = x.shape
         T = int(num_video_frames)
         assert B % T == 0 and cin == self.in_channels
+        down = 2 ** (len(self.channel_mult) - 1)
+        if H % down or W % down:
+            # the reference fails at th.cat([h, hs.pop()]) (video_model.py:483) when a stride-2 level rounds an odd size
+            raise RuntimeError(f"latent size {H}x{W} must be divisible by {down}: the skip connections of the "
+                               f"{len(self.channel_mult)}-level U-Net would not line up")
         nb = B // T
         self._check_indicator(image_only_indicator, nb, T)
         dev = x.device
