@@ -594,3 +594,68 @@ def test_unet_rejects_latents_whose_skips_would_not_line_up():
     xin, ts, ctx, y = _unet_inputs(2, 12)
     with pytest.raises(RuntimeError, match="divisible by 8"):
         net._prepare(xin, ts, ctx, y, None, 2, torch.zeros(2, 2))
+
+
+def test_non_square_latents_match_oracle():
+    """H != W through all three schedules (the reference handles any size divisible by the down-sampling factor): a
+    swapped height / width anywhere in the conv geometry, the upsample or the layout conversions shows up here."""
+    import emu_ops
+    from oracle import ref_decoder, ref_encoder, ref_unet, synth
+    from v3d_b200.encoder import Encoder
+
+    g = torch.Generator().manual_seed(9)
+    T, H, W = 2, 16, 24
+    net, sd = _build_unet()
+    xin = torch.randn(2 * T, 8, H, W, generator=g)
+    ts = torch.linspace(-0.5, 1.0, 2 * T)
+    ctx = torch.randn(2 * T, 1, 1024, generator=g)
+    y = torch.randn(2 * T, 768, generator=g)
+    with emu_ops.patched():
+        out = _run_unet(net, net._pack(torch.device("cpu")), xin, ts, ctx.reshape(2 * T, -1), y, T)
+    with torch.no_grad():
+        ref = ref_unet.unet_forward(sd, ref_unet.UNetSpec(model_channels=64), xin, ts, ctx, y, T, torch.zeros(2, T))
+    r = _rel(out, ref)
+    print("unet 16x24 rel-L2", r)
+    assert out.shape == ref.shape == (2 * T, 4, H, W) and r <= 3e-2 and _cos(out, ref) >= 0.999
+
+    dec, sdd = _build_decoder()
+    z = torch.randn(3, 4, 8, 16, generator=g)
+    with emu_ops.patched(), torch.no_grad():
+        out = dec._run(dec._pack(torch.device("cpu")), z, 3, 3, 1, 8, 16)
+        ref = ref_decoder.decoder_forward(sdd, ref_decoder.DecoderSpec(ch=64), z, 3)
+    r = _rel(out, ref)
+    print("decoder 8x16 rel-L2", r)
+    assert out.shape == ref.shape == (3, 3, 64, 128) and r <= 3e-2 and _cos(out, ref) >= 0.999
+
+    enc = Encoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4, 4],
+                  num_res_blocks=2, attn_resolutions=[], dropout=0.0, attn_type="vanilla")
+    sde = synth.synth_state_dict(enc.param_shapes(), seed=13)
+    enc.load_state_dict(sde, strict=True)
+    x = torch.randn(1, 3, 64, 128, generator=g)
+    with emu_ops.patched(), torch.no_grad():
+        out = enc.eval()._run(enc._pack(torch.device("cpu")), x)
+        ref = ref_encoder.encoder_forward(sde, ref_encoder.EncoderSpec(ch=64), x)
+    r = _rel(out, ref)
+    print("encoder 64x128 rel-L2", r)
+    assert out.shape == ref.shape == (1, 8, 8, 16) and r <= 3e-2 and _cos(out, ref) >= 0.999
+
+
+def test_decode_first_stage_chunking_matches_oracle():
+    """en_and_decode_n_samples_a_time < T: every chunk is decoded as its own short video (temporal convs zero-pad at
+    chunk edges, video_diffusion.py:182-210) - chunks of 2 + 1 frames vs the oracle's chunked decode, and != one chunk."""
+    import cpu_shims
+    import emu_ops
+    from oracle import ref_decoder
+
+    eng, _, sd_d = cpu_shims.cpu_engine(3, 2)
+    z = torch.randn(3, 4, 8, 8, generator=torch.Generator().manual_seed(2)) * 0.18215
+    with emu_ops.patched():
+        eng.en_and_decode_n_samples_a_time = 2
+        chunked = eng.decode_first_stage(z)
+        eng.en_and_decode_n_samples_a_time = 3
+        whole = eng.decode_first_stage(z)
+    with torch.no_grad():
+        ref = ref_decoder.decode_first_stage(sd_d, ref_decoder.DecoderSpec(ch=64), z, n_samples_a_time=2)
+    assert chunked.shape == ref.shape == (3, 3, 64, 64)
+    assert _rel(chunked, ref) <= 3e-2 and _cos(chunked, ref) >= 0.999
+    assert _rel(chunked, whole) > 1e-2          # the chunk boundary matters, exactly as in the reference
