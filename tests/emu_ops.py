@@ -9,7 +9,8 @@ offsets, fused-epilogue operands, halo buffers and exchanges) can be executed an
 Each function restates the CONTRACT documented in include/v3d_b200.h for one entry point, in plain torch: bf16 storage,
 arithmetic in fp64 (so that results do not depend on how a CPU BLAS blocks a given shape: a frame-sharded run and an
 unsharded run then agree to the last bit wherever the schedule is right), one rounding at the store.  It is only ever
-installed by `patched()` inside tests; nothing under v3d_b200/ imports it.
+installed by `patched()` inside tests; nothing under v3d_b200/ imports it.  The functions are device-agnostic, so
+tests/test_standins_gpu.py can hold each of them against the real kernel on the same CUDA tensors.
 """
 from __future__ import annotations
 
@@ -75,13 +76,13 @@ def gemm(a, w, out, *, K, N, rows_per_batch, batch=1, lda=None, ldb=None, ldd=No
         A = _strided(a, (batch, arows, K), (abs_, lda, 1)).double()
         nbb = batch if b_batch_stride else 1
         Bm = _strided(w, (nbb, N, taps * K), (b_batch_stride, ldb, 1)).double()
-        acc = torch.zeros(batch, rows_per_batch, N, dtype=torch.float64)
+        acc = torch.zeros(batch, rows_per_batch, N, dtype=torch.float64, device=a.device)
         for tap in range(taps):
             first = a_row0 + (tap - taps // 2) * tap_shift           # A row read by output row 0
             lo, hi = max(0, -first), min(rows_per_batch, arows - first)
             if hi <= lo:
                 continue
-            At = torch.zeros(batch, rows_per_batch, K, dtype=torch.float64)
+            At = torch.zeros(batch, rows_per_batch, K, dtype=torch.float64, device=a.device)
             At[:, lo:hi] = A[:, first + lo: first + hi]               # rows outside [0, a_rows) read as zero
             acc += At @ Bm[:, :, tap * K:(tap + 1) * K].transpose(1, 2)
         acc = acc.reshape(rows, N)
@@ -201,7 +202,7 @@ def attention_temporal_kv(q, kv, out, nb, tq, s, nheads, kv_row, kv_bstride, sca
     qm = _strided(q, (rows, c), (q.stride(0), 1)).double().reshape(nb, tq, s, nheads, 64)
     qm = qm.permute(0, 2, 3, 1, 4)                                                        # [b, s, h, tq, 64]
     idx = torch.tensor([[[kv_row[f] + b * kv_bstride[f] + p for f in range(tk)] for p in range(s)]
-                        for b in range(nb)])                                               # [b, s, tk] buffer rows
+                        for b in range(nb)], device=kv.device)                             # [b, s, tk] buffer rows
     kvm = kv.double()[idx]                                                                  # [b, s, tk, 2c]
     km = kvm[..., :c].reshape(nb, s, tk, nheads, 64).permute(0, 1, 3, 2, 4)
     vm = kvm[..., c:].reshape(nb, s, tk, nheads, 64).permute(0, 1, 3, 2, 4)
@@ -231,7 +232,7 @@ def im2col3x3(x, y, n, h, w, c, stride, pad, hout, wout, kpad):
     v = F.pad(v, (1, 1, 1, 1)) if pad else F.pad(v, (0, 1, 0, 1))
     cols = F.unfold(v, kernel_size=3, stride=stride)                                       # [n, c*9, L], (c, ky, kx)
     cols = cols.reshape(n, c, 9, hout * wout).permute(0, 3, 2, 1).reshape(n * hout * wout, 9 * c)   # (tap, c)
-    full = torch.zeros(n * hout * wout, kpad, dtype=torch.float64)
+    full = torch.zeros(n * hout * wout, kpad, dtype=torch.float64, device=x.device)
     full[:, : 9 * c] = cols
     _store(y.view(n * hout * wout, kpad), full)
     return y
@@ -274,7 +275,7 @@ def small_linear(x, w, bias, y, *, act_in=ACT_NONE, act_out=ACT_NONE, accumulate
 def timestep_embedding(t, out, dim, max_period=10000.0):
     _tick()
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t.float()[:, None] * freqs[None]                         # fp32 like the kernel and the reference
     out.copy_(torch.cat([torch.cos(args), torch.sin(args)], dim=-1))
     return out

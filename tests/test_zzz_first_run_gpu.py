@@ -31,6 +31,7 @@ GROUPS = {
                           "single_rank or view_sharded_engine_matches_unsharded_one_gpu_gloo or "
                           "cfg_split_engine_matches_unsharded_one_gpu_gloo"], 600),
     "fullsize_properties": ([str(TESTS / "test_fullsize_gpu.py")], 600),
+    "kernels_vs_standins": ([str(TESTS / "test_standins_gpu.py")], 300),
 }
 
 

@@ -39,6 +39,7 @@ for stage in "$@"; do
       run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo or single_rank"   # incl. the cfg / cfg+views plans
       run 900 first_parity.log $PY -m pytest tests/test_parity_gpu.py -m gpu -q -s -k "encoder or heun or vanilla or central"
       run 900 first_fullsize.log $PY -m pytest tests/test_fullsize_gpu.py -m gpu -q -s
+      run 300 first_standins.log $PY -m pytest tests/test_standins_gpu.py -m gpu -q
       unset V3D_RUN_UNVALIDATED ;;
     pair)
       # the staged bring-up probe first: bounded waits, names the primitive that misbehaves instead of hanging
