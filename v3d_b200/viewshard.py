@@ -92,11 +92,14 @@ class ViewShard:
         return row, bstride
 
     # ---- transport ------------------------------------------------------------------------------
-    def _via_host(self, t: torch.Tensor) -> bool:
-        """gloo cannot move CUDA memory for every primitive: stage through the host (tests only; NCCL is direct)."""
+    def _is_gloo(self) -> bool:
         if self._staged is None:
             self._staged = dist.get_backend(self.group) == "gloo"
-        return self._staged and t.is_cuda
+        return self._staged
+
+    def _via_host(self, t: torch.Tensor) -> bool:
+        """gloo cannot move CUDA memory for every primitive: stage through the host (tests only; NCCL is direct)."""
+        return self._is_gloo() and t.is_cuda
 
     def _count(self, kind: str) -> None:
         self.exchanges[kind] = self.exchanges.get(kind, 0) + 1
@@ -133,6 +136,7 @@ class ViewShard:
         if self.world == 1:
             return pad
         staged = self._via_host(pad)
+        tagged = self._is_gloo()
         ops, landing = [], []
         for b in range(nb):
             for peer, send_idx, recv_idx, tag_s, tag_r in ((prev_r, 1, 0, 0, 1), (next_r, tl, tl + 1, 1, 0)):
@@ -145,9 +149,12 @@ class ViewShard:
                     landing.append((dst, host))
                     dst = host
                 g = self._global_rank(peer)
-                # a frame sent "towards lower ranks" (tag_s 0) is received by the peer as its right halo (tag_r 0)
-                ops.append(dist.P2POp(dist.isend, src, g, group=self.group, tag=2 * b + tag_s))
-                ops.append(dist.P2POp(dist.irecv, dst, g, group=self.group, tag=2 * b + tag_r))
+                # a frame sent "towards lower ranks" (tag_s 0) is received by the peer as its right halo (tag_r 0).
+                # Tags disambiguate the messages on gloo; NCCL matches sends and receives of a pair in issue order
+                # (the order here is the same on both sides) and takes no tags.
+                ts_, tr_ = (2 * b + tag_s, 2 * b + tag_r) if tagged else (0, 0)
+                ops.append(dist.P2POp(dist.isend, src, g, group=self.group, tag=ts_))
+                ops.append(dist.P2POp(dist.irecv, dst, g, group=self.group, tag=tr_))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         for dst, host in landing:
