@@ -659,3 +659,40 @@ def test_decode_first_stage_chunking_matches_oracle():
     assert chunked.shape == ref.shape == (3, 3, 64, 64)
     assert _rel(chunked, ref) <= 3e-2 and _cos(chunked, ref) >= 0.999
     assert _rel(chunked, whole) > 1e-2          # the chunk boundary matters, exactly as in the reference
+
+
+def test_do_sample_call_sequence_runs_against_the_drop_in_engine():
+    """SURVEY 8(f)-3, second caller: the body of sgm/inference/helpers.py:do_sample (:121-170) touches
+    model.ema_scope(), model.conditioner.get_unconditional_conditioning, model.denoiser(model.model, ...), the sampler
+    call and model.decode_first_stage - replayed here statement by statement against the drop-in engine (kernels as
+    CPU stand-ins) and compared with sample_views on the same conditioning."""
+    import math
+
+    import cpu_shims
+    import emu_ops
+    from v3d_b200 import conditioning
+
+    T, hw = 3, 8
+    eng, _, _ = cpu_shims.cpu_engine(T, 2)
+    eng.conditioner = conditioning.GeneralConditioner(conditioning.V3D_512_EMB_MODELS)
+    g = torch.Generator().manual_seed(11)
+    clip_emb, latent = torch.randn(1, 1, 1024, generator=g), torch.randn(1, 4, hw, hw, generator=g)
+    with emu_ops.patched(), torch.no_grad(), eng.ema_scope():
+        c, uc = conditioning.assemble_v3d_conditioning(eng.conditioner, clip_emb, latent, 6.0, 127.0, 0.02, T)
+        num_samples = [T]
+        for k in c:                                                    # helpers.py:143-147
+            if not k == "crossattn":
+                c[k], uc[k] = map(lambda y: y[k][: math.prod(num_samples)], (c, uc))
+        additional_model_inputs = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+        randn = torch.randn((T, 4, hw, hw), generator=g)
+
+        def denoiser(input, sigma, cc):                                # helpers.py:156-159
+            return eng.denoiser(eng.model, input, sigma, cc, **additional_model_inputs)
+
+        samples_z = eng.sampler(denoiser, randn.clone(), cond=c, uc=uc)
+        eng.en_and_decode_n_samples_a_time = T
+        samples_x = eng.decode_first_stage(samples_z)
+        samples = torch.clamp((samples_x + 1.0) / 2.0, min=0.0, max=1.0)
+        ref = eng.sample_views(randn.clone(), c, uc, num_frames=T)
+    assert samples.shape == (T, 3, 8 * hw, 8 * hw) and float(samples.min()) >= 0.0 and float(samples.max()) <= 1.0
+    assert torch.equal(samples_x, ref)

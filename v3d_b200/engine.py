@@ -6,6 +6,7 @@ EMA, losses, loggers) are out of scope.
 """
 from __future__ import annotations
 
+import contextlib
 import copy
 import math
 from typing import Dict, Optional
@@ -102,6 +103,13 @@ class DiffusionEngine(nn.Module):
         sd = {k: v for k, v in sd.items() if k not in own or tuple(own[k].shape) == tuple(v.shape)}
         missing, unexpected = self.load_state_dict(sd, strict=False)
         print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
+
+    @contextlib.contextmanager
+    def ema_scope(self, context=None):
+        """`with model.ema_scope():` of the reference's callers (sgm/inference/helpers.py:123, video_diffusion.py:324-338
+        swaps in the EMA weights when `use_ema`); this engine is inference-only and holds one set of weights, so the
+        scope is a no-op - it exists so that `do_sample` runs against the drop-in engine unchanged."""
+        yield None
 
     @torch.no_grad()
     def decode_first_stage(self, z: torch.Tensor) -> torch.Tensor:
