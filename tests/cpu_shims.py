@@ -8,6 +8,7 @@ Used by tests/test_host_schedule_cpu.py only.
 import torch
 
 from v3d_b200.decoder import VideoDecoder
+from v3d_b200.encoder import Encoder
 from v3d_b200.sampling import EulerEDMSampler, HeunEDMSampler
 from v3d_b200.unet import VideoUNet
 
@@ -32,6 +33,14 @@ class CpuDecoder(VideoDecoder):
             self._packed = self._pack(CPU)
         with torch.no_grad():
             return self._run(self._packed, z, B, T, B // T, H, W)
+
+
+class CpuEncoder(Encoder):
+    def forward(self, x):
+        if self._packed is None:
+            self._packed = self._pack(CPU)
+        with torch.no_grad():
+            return self._run(self._packed, x)
 
 
 class CpuEuler(EulerEDMSampler):

@@ -696,3 +696,45 @@ def test_do_sample_call_sequence_runs_against_the_drop_in_engine():
         ref = eng.sample_views(randn.clone(), c, uc, num_frames=T)
     assert samples.shape == (T, 3, 8 * hw, 8 * hw) and float(samples.min()) >= 0.0 and float(samples.max()) <= 1.0
     assert torch.equal(samples_x, ref)
+
+
+def test_encode_first_stage_matches_oracle():
+    """DiffusionEngine.encode_first_stage (video_diffusion.py:212-237) with the native Encoder: chunked encode of a
+    [b, t, c, h, w] video, posterior sample drawn on the CPU generator like the reference (distributions.py:37-41),
+    times scale_factor - against the oracle encoder + Gaussian sample with the same draws."""
+    import cpu_shims
+    import emu_ops
+    from oracle import ref_encoder, synth
+    from v3d_b200 import engine
+
+    cfg = engine.v3d_512_config(num_frames=2, num_steps=1)
+    cfg["network_config"]["params"]["model_channels"] = 64
+    fs = cfg["first_stage_config"]["params"]
+    fs["decoder_config"]["params"]["ch"] = 64
+    fs["encoder_config"] = {"target": "v3d_b200.sgm.modules.diffusionmodules.model.Encoder",
+                            "params": dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256,
+                                           in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+                                           attn_resolutions=[], dropout=0.0)}
+    fs["regularizer_config"] = {"target": "v3d_b200.encoder.DiagonalGaussianRegularizer", "params": {"sample": True}}
+    eng = engine.DiffusionEngine(**cfg).eval()
+    enc = eng.first_stage_model.encoder
+    assert enc is not None, "native encoder not built"
+    sd = synth.synth_state_dict(enc.param_shapes(), seed=21)
+    enc.load_state_dict(sd, strict=True)
+    enc.__class__ = cpu_shims.CpuEncoder
+    x = torch.randn(1, 3, 3, 64, 64, generator=torch.Generator().manual_seed(6))     # [b, t, c, h, w]
+    eng.en_and_decode_n_samples_a_time = 2                                            # chunks of 2 + 1 frames
+    with emu_ops.patched():
+        torch.manual_seed(77)
+        z = eng.encode_first_stage(x)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        flat = x.reshape(-1, 3, 64, 64)
+        zs = []
+        for chunk in (flat[:2], flat[2:]):
+            mom = ref_encoder.encoder_forward(sd, ref_encoder.EncoderSpec(ch=64), chunk)
+            zs.append(ref_encoder.gaussian_sample(mom, torch.randn(chunk.shape[0], 4, 8, 8)))
+        ref = 0.18215 * torch.cat(zs)
+    r = _rel(z, ref)
+    print("encode_first_stage vs oracle: rel-L2", r)
+    assert z.shape == ref.shape == (3, 4, 8, 8) and r <= 3e-2

@@ -129,6 +129,21 @@ class DiffusionEngine(nn.Module):
         return out
 
     @torch.no_grad()
+    def encode_first_stage(self, x: torch.Tensor) -> torch.Tensor:
+        """video_diffusion.py:212-237: images (or a [b,t,c,h,w] video, flattened and NOT folded back, as in the
+        reference) -> scale_factor * first_stage_model.encode(.), in chunks of `en_and_decode_n_samples_a_time`.
+        Needs the native encoder (AutoencodingEngine built with `encoder_config.target` = this package's Encoder)."""
+        if self.input_key == "latents":
+            return x * self.scale_factor
+        if x.dim() == 5:
+            x = x.reshape(-1, *x.shape[2:])
+        n_samples = self.en_and_decode_n_samples_a_time or x.shape[0]
+        outs = [self.first_stage_model.encode(x[n * n_samples:(n + 1) * n_samples])
+                for n in range(math.ceil(x.shape[0] / n_samples))]
+        z = torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+        return self.scale_factor * z
+
+    @torch.no_grad()
     def sample_views(self, randn: torch.Tensor, c: Dict, uc: Dict, num_frames: int,
                      decoding_t: Optional[int] = None, view_shard=None, shard=None) -> torch.Tensor:
         """The hot path of sample_one (scripts/pub/V3D_512.py:269-285): sampler loop + first-stage decode.
