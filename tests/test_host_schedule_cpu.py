@@ -738,3 +738,61 @@ def test_encode_first_stage_matches_oracle():
     r = _rel(z, ref)
     print("encode_first_stage vs oracle: rel-L2", r)
     assert z.shape == ref.shape == (3, 4, 8, 8) and r <= 3e-2
+
+
+def test_views_from_image_matches_oracle_composition():
+    """sample_one from the conditioning image to the decoded views (V3D_512.py:235-285), CLIP embedding given: native
+    encoder -> cond_aug noise -> conditioner + per-frame repeat -> latent noise -> sampler + decode, with the reference's
+    order of random draws - against the same composition of the oracle's pieces under the same seed."""
+    import cpu_shims
+    import emu_ops
+    from oracle import ref_conditioning, ref_decoder, ref_encoder, ref_sampling, ref_unet, synth
+    from v3d_b200 import conditioning, engine, pipeline
+
+    T, steps, side = 3, 2, 64
+    cfg = engine.v3d_512_config(num_frames=T, num_steps=steps, min_cfg=1.5, max_cfg=3.5)
+    cfg["network_config"]["params"]["model_channels"] = 64
+    fs = cfg["first_stage_config"]["params"]
+    fs["decoder_config"]["params"]["ch"] = 64
+    fs["encoder_config"] = {"target": "v3d_b200.sgm.modules.diffusionmodules.model.Encoder",
+                            "params": dict(attn_type="vanilla", double_z=True, z_channels=4, resolution=256,
+                                           in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+                                           attn_resolutions=[], dropout=0.0)}
+    fs["regularizer_config"] = {"target": "v3d_b200.encoder.DiagonalGaussianRegularizer", "params": {"sample": True}}
+    eng = engine.DiffusionEngine(**cfg).eval()
+    eng.conditioner = conditioning.GeneralConditioner(conditioning.V3D_512_EMB_MODELS)
+    unet, dec, enc = eng.model.diffusion_model, eng.first_stage_model.decoder, eng.first_stage_model.encoder
+    sd_u = synth.synth_state_dict(unet.param_shapes(), seed=11)
+    sd_d = synth.synth_state_dict(dec.param_shapes(), seed=12)
+    sd_e = synth.synth_state_dict(enc.param_shapes(), seed=13)
+    unet.load_state_dict(sd_u, strict=True)
+    dec.load_state_dict(sd_d, strict=True)
+    enc.load_state_dict(sd_e, strict=True)
+    unet.__class__, dec.__class__, enc.__class__ = cpu_shims.CpuUNet, cpu_shims.CpuDecoder, cpu_shims.CpuEncoder
+    eng.sampler.__class__ = cpu_shims.CpuEuler
+    g = torch.Generator().manual_seed(31)
+    image = torch.rand(1, 3, side, side, generator=g) * 2 - 1
+    clip_emb = torch.randn(1, 1, 1024, generator=g)
+
+    torch.manual_seed(23)
+    with emu_ops.patched():
+        frames = pipeline.views_from_image(eng, image, clip_emb, num_frames=T, fps_id=6, motion_bucket_id=127,
+                                           cond_aug=0.02)
+    torch.manual_seed(23)
+    with torch.no_grad():
+        mom = ref_encoder.encoder_forward(sd_e, ref_encoder.EncoderSpec(ch=64), image)
+        latent = ref_encoder.gaussian_sample(mom, torch.randn(1, 4, side // 8, side // 8))   # posterior draw
+        latent = latent + 0.02 * torch.randn_like(latent)                                   # cond_aug noise
+        c, uc = ref_conditioning.v3d_conditioning(clip_emb, latent, 6, 127, 0.02, T)
+        randn = torch.randn(T, 4, side // 8, side // 8)                                       # latent noise
+        extra = {"image_only_indicator": torch.zeros(2, T), "num_video_frames": T}
+        z = ref_sampling.euler_edm_sample(
+            lambda i, s, cc: ref_sampling.denoiser(
+                lambda xx, tt, cond, **kw: ref_unet.openai_wrapper(sd_u, ref_unet.UNetSpec(model_channels=64), xx, tt,
+                                                                   cond, **kw), i, s, cc, **extra),
+            randn, c, uc, steps, ref_sampling.guider_scale(1.5, 3.5, T), T)
+        ref = ref_decoder.decode_first_stage(sd_d, ref_decoder.DecoderSpec(ch=64), z, n_samples_a_time=T)
+    r, cs = _rel(frames, ref), _cos(frames, ref)
+    print("views_from_image vs oracle composition: rel-L2", r, "cos", cs)
+    assert frames.shape == ref.shape == (T, 3, side, side)
+    assert r <= 5e-2 and cs >= 0.998
