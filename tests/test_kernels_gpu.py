@@ -421,6 +421,20 @@ def test_gemm_cta_pair_path_subprocess():
 
 
 @_unvalidated
+def test_gemm_tma_staged_residual_subprocess():
+    """EPI_BF16RT (V3D_GEMM_RTMA=1, read once per process): the single residual of a bf16-output GEMM / conv arrives as
+    128 x 32 TMA sub-tiles two sub-tiles ahead instead of per-lane global loads.  The GEMM / conv / temporal-conv tests
+    of this file (several carry R1, some in place) re-run in a child with the switch on, under a hard timeout."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, V3D_GEMM_RTMA="1", V3D_RUN_UNVALIDATED="0")
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
+                          "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+@_unvalidated
 @pytest.mark.parametrize("poly", [1, 2, 3])
 def test_attention_poly_exp2_subprocess(poly):
     """FMA-pipe exp2 for 2 / 4 / 6 of a tile's 8 key chunks (V3D_ATTN_POLY, read once per process): the spatial

@@ -10,6 +10,7 @@
 #   firstrun      the not-yet-validated groups directly (V3D_RUN_UNVALIDATED=1), one child process each, verbose
 #   pair          cta_group::2 GEMM tiles (V3D_GEMM_2CTA=1) under a 300 s timeout, then the per-shape microbenchmark
 #                 with the switch off / on
+#   rtma          TMA-staged residual epilogue (V3D_GEMM_RTMA=1): tests, then per-shape timings
 #   attn_poly     FMA-pipe exp2 variants of the spatial attention (V3D_ATTN_POLY=1..3): tests, then timings 0..3
 #   bench         bench.py (default N=1) -> gpurun_out/bench.json ; bench.py --impl reference -> bench_ref.json
 #   sweep         BASELINE configs[4]: S in {10,25,50} x T in {14,18,25} on one GPU -> gpurun_out/sweep.json
@@ -49,6 +50,11 @@ for stage in "$@"; do
       V3D_RUN_UNVALIDATED=1 run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
       run 300 micro_single.log $PY tools/microbench.py gemm conv
       V3D_GEMM_2CTA=1 run 300 micro_pair.log $PY tools/microbench.py gemm conv ;;
+    rtma)
+      # TMA-staged residual epilogue (V3D_GEMM_RTMA=1): tests under a timeout (a barrier-phase mistake would hang),
+      # then the per-shape microbenchmark with the switch off / on (the +R1 rows are the ones that should move)
+      V3D_RUN_UNVALIDATED=1 run 400 rtma_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "tma_staged_residual"
+      V3D_GEMM_RTMA=1 run 300 micro_rtma.log $PY tools/microbench.py gemm conv ;;
     attn_poly)
       V3D_RUN_UNVALIDATED=1 run 600 attn_poly_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "attention_poly_exp2"
       for k in 0 1 2 3; do V3D_ATTN_POLY=$k run 300 "micro_attn_poly$k.log" $PY tools/microbench.py attn; done ;;

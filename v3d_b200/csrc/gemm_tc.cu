@@ -58,12 +58,14 @@ struct GemmEpi {
 
 // NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN tile;
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader's tensor core reads both halves.
-template <int BN, int NCTA = 1>
+template <int BN, int NCTA = 1, bool RT = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 8 * 4096;  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled
+  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled; RT adds the same again for the TMA-staged residual sub-tiles
+  static constexpr int OUT_STAGING_BYTES = 8 * 4096;
+  static constexpr int STAGING_BYTES = (RT ? 2 : 1) * OUT_STAGING_BYTES;
   static constexpr int NSTAGE_RAW = (kSmemBudget - 2048 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
   // accumulator ring in TMEM: as many stages as fit in the 512 columns (max 4). Deeper rings let the MMA issuer run
@@ -77,6 +79,9 @@ struct Cfg {
 // epilogue variants (compile-time): what is stored and how
 constexpr int EPI_BF16 = 0;   // bf16 sub-tiles staged in shared memory, written by TMA; at most one residual (R1)
 constexpr int EPI_BF16R2 = 4; // as EPI_BF16 with both residuals (blend epilogue); the only variant that carries R2
+constexpr int EPI_BF16RT = 5; // as EPI_BF16 with R1 always present and staged by TMA: the residual sub-tile (128 rows x 32
+                              // columns) lands in shared memory two sub-tiles ahead of its use instead of arriving
+                              // through per-lane global loads one load group ahead (opt-in: V3D_GEMM_RTMA=1)
 constexpr int EPI_GEGLU = 1;  // value * gelu(gate) then as EPI_BF16 (linear mode only)
 constexpr int EPI_F32 = 2;    // fp32 direct stores (optional SiLU)
 constexpr int EPI_TRANS = 3;  // fp32 transposed store with per-row bias (small-M mode, linear only)
@@ -134,8 +139,10 @@ __device__ __forceinline__ void tile_origin(const GemmEpi& p, int m_tile, int& t
 template <int BN, bool CONV, int EPI, int NCTA = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapD, const GemmEpi p) {
-  using C = Cfg<BN, NCTA>;
+               const __grid_constant__ CUtensorMap mapD, const GemmEpi p, const __grid_constant__ CUtensorMap mapR) {
+  constexpr bool RTMA = EPI == EPI_BF16RT;
+  static_assert(!RTMA || NCTA == 1, "the TMA-staged residual variant is single-CTA");
+  using C = Cfg<BN, NCTA, RTMA>;
   static_assert(NCTA == 1 || NCTA == 2, "one CTA or a CTA pair");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -145,7 +152,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* empty_bar = full_bar + C::NSTAGE;
   uint64_t* tfull_bar = empty_bar + C::NSTAGE;
   uint64_t* tempty_bar = tfull_bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
+  uint64_t* rfull_bar = tempty_bar + 4;  // RTMA only: [group][buffer], one TMA transaction each
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4 + (RTMA ? 4 : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,7 +161,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    if (EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU) tma_prefetch_desc(&mapD);
+    if (EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU || RTMA) tma_prefetch_desc(&mapD);
+    if (RTMA) {
+      tma_prefetch_desc(&mapR);
+      for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
+    }
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -288,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // bias/residual loads issued underneath it, math, then either the swizzled smem slab (32 rows x 128 B per
     // warp, flushed as row-contiguous 16-byte stores: 4 full 128-byte lines per warp instruction) or direct fp32.
     constexpr bool GEGLU = EPI == EPI_GEGLU;
-    constexpr bool STAGED = EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU;
+    constexpr bool STAGED = EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU || RTMA;
     constexpr bool DUAL = EPI == EPI_BF16R2 || EPI == EPI_F32;  // variants that may take a second residual
     constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
     constexpr int NCH = OUT_COLS / 16;
@@ -300,11 +312,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int NSUB = OUT_COLS / SUBW;
     constexpr int CH_HALF = ((NSUB + 1) / 2) * CPS;
     constexpr int SUB_BYTES = BM * SUBW * 2;
-    static_assert(2 * 2 * SUB_BYTES <= C::STAGING_BYTES, "staging too small");
+    static_assert(2 * 2 * SUB_BYTES <= C::OUT_STAGING_BYTES, "staging too small");
+    static_assert(!RTMA || SUBW == 32, "the TMA-staged residual needs 32-column sub-tiles");
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
     const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(half * 2 * SUB_BYTES);  // this group's buffers
+    // RTMA: this group's two residual buffers (same 128 x 64 B, 64B-swizzled layout as the output buffers) + barriers
+    uint8_t* const rbuf = staging + C::OUT_STAGING_BYTES + half * 2 * SUB_BYTES;
+    uint64_t* const rfull = rfull_bar + half * 2;
     const bool store_leader = q == 0 && lane == 0;
     const uint32_t row_off = static_cast<uint32_t>(r * SUBW * 2);
     const uint32_t swz = SUBW == 32 ? static_cast<uint32_t>((r >> 1) & 3) : 0u;  // 64B-swizzle XOR of the 16-byte chunk
@@ -450,12 +466,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int hh = 0; hh < LG; ++hh) na[hh][0] = na[hh][1] = make_uint4(0, 0, 0, 0);
       auto load_res = [&](int g) {
+        if (RTMA) return;  // the residual sub-tiles arrive through TMA (below)
 #pragma unroll
         for (int hh = 0; hh < LG; ++hh) {
           const int c = (c_begin + g * LG + hh) * 16;
           if (r1p) { na[hh][0] = __ldg(reinterpret_cast<const uint4*>(r1p + c)); na[hh][1] = __ldg(reinterpret_cast<const uint4*>(r1p + c) + 1); }
         }
       };
+      // RTMA: the group's store leader requests residual sub-tile `sub` (index within this tile's share) into the
+      // buffer the sub-tile counter selects; the TMA clips at row / image tails like the output store (zero fill)
+      auto request_res = [&](int col0, int o0, int o1, int o2, uint32_t slot) {
+        uint8_t* dst = rbuf + (slot & 1u) * SUB_BYTES;
+        mbar_arrive_expect_tx(&rfull[slot & 1u], SUB_BYTES);
+        if (CONV) tma_load_4d(dst, &mapR, &rfull[slot & 1u], col0, o0, o1, o2);
+        else tma_load_3d(dst, &mapR, &rfull[slot & 1u], col0, o1, o0);
+      };
+      // the first two sub-tiles of a tile are requested at the end of the previous tile (below); only the very first
+      // tile of this CTA requests its own
+      if (RTMA && store_leader && iter == 0) {
+        if (my_n > 0) request_res(obase + c_begin * 16, t0, t1, t2, nstore);
+        if (LG < my_n) request_res(obase + (c_begin + LG) * 16, t0, t1, t2, nstore + 1);
+      }
       if (my_n > 0) load_res(0);
 #pragma unroll
       for (int g = 0; g < NG_HALF; ++g) {
@@ -464,10 +495,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           V3D_ETRACE();  // group: TMEM data landed
           if ((g + 1) * LG < my_n) issue_group(g + 1, vb[(g + 1) & 1]);
           uint4 ca[LG][2], cb[LG][2];
+          if (RTMA) mbar_wait(&rfull[nstore & 1u], (nstore >> 1) & 1u);  // this sub-tile's residual rows have landed
 #pragma unroll
           for (int hh = 0; hh < LG; ++hh) {
-            ca[hh][0] = na[hh][0];
-            ca[hh][1] = na[hh][1];
+            if (RTMA) {
+              const uint32_t rrow = smem_u32(rbuf) + (nstore & 1u) * SUB_BYTES + row_off;
+              ca[hh][0] = lds128(rrow + (((hh * 2) ^ swz) << 4));
+              ca[hh][1] = lds128(rrow + (((hh * 2 + 1) ^ swz) << 4));
+            } else {
+              ca[hh][0] = na[hh][0];
+              ca[hh][1] = na[hh][1];
+            }
             cb[hh][0] = cb[hh][1] = make_uint4(0, 0, 0, 0);
             // the second residual (blend epilogue only) is fetched for the current group: its rows were pulled
             // into L2 two tiles ago, and holding a second prefetched set would spill
@@ -608,11 +646,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   bulk_commit();
                 }
                 V3D_ETRACE();  // sub-tile handed to TMA
+                // RTMA: every thread of the group read this sub-tile's residual buffer before the barrier above, so
+                // the buffer can take the sub-tile after next
+                if (RTMA && store_leader && (g + 2) * LG < my_n)
+                  request_res(obase + (c_begin + (g + 2) * LG) * 16, t0, t1, t2, nstore);
                 ++nstore;
               }
             }
           }
         }
+      }
+      if (RTMA && store_leader && tile + static_cast<int>(gridDim.x) / NCTA < total_tiles) {
+        // both residual buffers are free now (every thread of the group passed the last sub-tile's barrier): request
+        // the head of the NEXT tile's share, so that it is in shared memory before that tile's accumulator is ready
+        int u0, u1, u2;
+        tile_origin<CONV>(p, tw.m_tile * NCTA + cta_rank, u0, u1, u2);
+        const int hsel_next = (NSUB & 1) ? (half ^ ((iter + 1) & 1)) : half;
+        const int my_n_next = hsel_next ? NCH - CH_HALF : CH_HALF;
+        const int col_next = tw.n_tile * OUT_COLS + c_begin_next * 16;
+        if (my_n_next > 0) request_res(col_next, u0, u1, u2, nstore);
+        if (LG < my_n_next) request_res(col_next + LG * 16, u0, u1, u2, nstore + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -656,8 +709,9 @@ static int pick_block_n(int N, int act) {
 
 template <int BN, bool CONV, int EPI, int NCTA = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmEpi& epi,
-                  cudaStream_t st) {
-  using C = Cfg<BN, NCTA>;
+                  cudaStream_t st, const CUtensorMap* mr = nullptr) {
+  using C = Cfg<BN, NCTA, EPI == EPI_BF16RT>;
+  const CUtensorMap& mres = mr ? *mr : md;  // only the EPI_BF16RT instantiations read it
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, CONV, EPI, NCTA>;
   if (!configured) {
@@ -671,7 +725,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   if (NCTA == 1) {
     const int total = epi.num_m_tiles * epi.num_n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi);
+    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi, mres);
   } else {
     // one cluster of two CTAs per 256-row pair tile, persistent over at most num_sms / 2 clusters
     const int total = ((epi.num_m_tiles + 1) / 2) * epi.num_n_tiles;
@@ -689,7 +743,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, epi);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, epi, mres);
     if (e != cudaSuccess) {
       set_error("gemm_tc_kernel (CTA pair) launch failed: %s", cudaGetErrorString(e));
       return V3D_ERR_CUDA;
@@ -719,9 +773,14 @@ static int dispatch_epi_pair(int epi_kind, const CUtensorMap& ma, const CUtensor
 
 template <int BN, bool CONV>
 static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                        const GemmEpi& epi, cudaStream_t st) {
+                        const GemmEpi& epi, cudaStream_t st, const CUtensorMap* mr = nullptr) {
   switch (epi_kind) {
     case EPI_BF16: return launch<BN, CONV, EPI_BF16>(ma, mb, md, epi, st);
+    case EPI_BF16RT:
+      if constexpr (BN % 32 == 0 && BN >= 64) {
+        if (mr != nullptr) return launch<BN, CONV, EPI_BF16RT>(ma, mb, md, epi, st, mr);
+      }
+      break;
     case EPI_BF16R2: return launch<BN, CONV, EPI_BF16R2>(ma, mb, md, epi, st);
     case EPI_F32: return launch<BN, CONV, EPI_F32>(ma, mb, md, epi, st);
     case EPI_GEGLU:
@@ -737,7 +796,7 @@ static int dispatch_epi(int epi_kind, const CUtensorMap& ma, const CUtensorMap& 
 
 template <bool CONV>
 static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                       const GemmEpi& epi, cudaStream_t st, bool pair = false) {
+                       const GemmEpi& epi, cudaStream_t st, bool pair = false, const CUtensorMap* mr = nullptr) {
   if (pair) {
     switch (bn) {
       case 256: return dispatch_epi_pair<256, CONV>(epi_kind, ma, mb, md, epi, st);
@@ -747,12 +806,12 @@ static int dispatch_bn(int bn, int epi_kind, const CUtensorMap& ma, const CUtens
     }
   }
   switch (bn) {
-    case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, md, epi, st);
-    case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, md, epi, st);
-    case 128: return dispatch_epi<128, CONV>(epi_kind, ma, mb, md, epi, st);
-    case 64: return dispatch_epi<64, CONV>(epi_kind, ma, mb, md, epi, st);
-    case 32: return dispatch_epi<32, CONV>(epi_kind, ma, mb, md, epi, st);
-    case 16: return dispatch_epi<16, CONV>(epi_kind, ma, mb, md, epi, st);
+    case 256: return dispatch_epi<256, CONV>(epi_kind, ma, mb, md, epi, st, mr);
+    case 160: return dispatch_epi<160, CONV>(epi_kind, ma, mb, md, epi, st, mr);
+    case 128: return dispatch_epi<128, CONV>(epi_kind, ma, mb, md, epi, st, mr);
+    case 64: return dispatch_epi<64, CONV>(epi_kind, ma, mb, md, epi, st, mr);
+    case 32: return dispatch_epi<32, CONV>(epi_kind, ma, mb, md, epi, st, mr);
+    case 16: return dispatch_epi<16, CONV>(epi_kind, ma, mb, md, epi, st, mr);
     default: set_error("unsupported block_n %d", bn); return V3D_ERR_BAD_ARG;
   }
 }
@@ -1017,7 +1076,21 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     e.R2 = nullptr;
   }
   if (epi_kind == EPI_BF16 && e.R2 != nullptr) epi_kind = EPI_BF16R2;
-  if (epi_kind == EPI_BF16 || epi_kind == EPI_BF16R2 || epi_kind == EPI_GEGLU) {
+  // TMA-staged residual: opt-in (V3D_GEMM_RTMA=1) until timed on hardware; single residual, 32-column sub-tiles, one CTA
+  bool rtma = false;
+  {
+    static int want_rtma = -1;
+    if (want_rtma < 0) {
+      const char* v = getenv("V3D_GEMM_RTMA");
+      want_rtma = (v && atoi(v) != 0) ? 1 : 0;
+    }
+    rtma = want_rtma == 1 && epi_kind == EPI_BF16 && e.R1 != nullptr && !pair && bn % 32 == 0 && bn >= 64 &&
+           (reinterpret_cast<uintptr_t>(e.R1) & 15u) == 0;
+  }
+  if (rtma) epi_kind = EPI_BF16RT;
+  CUtensorMap mr;
+  memset(&mr, 0, sizeof(mr));
+  if (epi_kind == EPI_BF16 || epi_kind == EPI_BF16R2 || epi_kind == EPI_GEGLU || epi_kind == EPI_BF16RT) {
     const uint64_t out_cols = static_cast<uint64_t>(e.num_n_tiles) * (epi_kind == EPI_GEGLU ? bn / 2 : bn);
     const uint32_t ocols_tile = epi_kind == EPI_GEGLU ? bn / 2 : bn;
     const uint32_t subw = ocols_tile % 32 == 0 ? 32 : 16;  // must match SUBW in the kernel
@@ -1034,7 +1107,21 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       rc = make_tmap_bf16(&md, a->D, 3, dims, str, box, swz);
     }
     if (rc) return rc;
+    if (rtma) {  // the residual through the same geometry as the output: [cols][rows...] with row stride ldr1
+      if (conv) {
+        const uint64_t dims[4] = {out_cols, (uint64_t)e.cw, (uint64_t)e.ch, (uint64_t)e.cn};
+        const uint64_t str[3] = {(uint64_t)e.ldr1 * 2, (uint64_t)e.ldr1 * 2 * e.cw, (uint64_t)e.ldr1 * 2 * e.cw * e.ch};
+        const uint32_t box[4] = {subw, (uint32_t)e.bw, (uint32_t)e.bh, (uint32_t)e.bn};
+        rc = make_tmap_bf16(&mr, e.R1, 4, dims, str, box, swz);
+      } else {
+        const uint64_t dims[3] = {out_cols, (uint64_t)e.rows_per_batch, (uint64_t)e.batch};
+        const uint64_t str[2] = {(uint64_t)e.ldr1 * 2, (uint64_t)e.ldr1 * 2 * e.rows_per_batch};
+        const uint32_t box[3] = {subw, BM, 1};
+        rc = make_tmap_bf16(&mr, e.R1, 3, dims, str, box, swz);
+      }
+      if (rc) return rc;
+    }
   }
-  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st, pair)
-              : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st, pair);
+  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr)
+              : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr);
 }
