@@ -63,9 +63,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled; RT adds the same again for the TMA-staged residual sub-tiles
+  // 4 KB per epilogue warp: 32 rows x 128 B, swizzled; RT adds a ring of RDEPTH residual sub-tiles (8 KB each) per group
   static constexpr int OUT_STAGING_BYTES = 8 * 4096;
-  static constexpr int STAGING_BYTES = (RT ? 2 : 1) * OUT_STAGING_BYTES;
+  static constexpr int RDEPTH = 3;
+  static constexpr int STAGING_BYTES = OUT_STAGING_BYTES + (RT ? 2 * RDEPTH * 8192 : 0);
   static constexpr int NSTAGE_RAW = (kSmemBudget - 2048 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
   // accumulator ring in TMEM: as many stages as fit in the 512 columns (max 4). Deeper rings let the MMA issuer run
@@ -73,7 +74,7 @@ struct Cfg {
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 160 ? 160 : 256)));
   static constexpr int ACC_STAGES = (512 / ACC_STRIDE) > 4 ? 4 : (512 / ACC_STRIDE);
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + (RT ? 512 : 256) /*barriers*/;
 };
 
 // epilogue variants (compile-time): what is stored and how
@@ -152,8 +153,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* empty_bar = full_bar + C::NSTAGE;
   uint64_t* tfull_bar = empty_bar + C::NSTAGE;
   uint64_t* tempty_bar = tfull_bar + 4;
-  uint64_t* rfull_bar = tempty_bar + 4;  // RTMA only: [group][buffer], one TMA transaction each
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4 + (RTMA ? 4 : 0));
+  uint64_t* rfull_bar = tempty_bar + 4;  // RTMA only: [group][ring slot], one TMA transaction each
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4 + (RTMA ? 2 * C::RDEPTH : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (EPI == EPI_BF16 || EPI == EPI_BF16R2 || EPI == EPI_GEGLU || RTMA) tma_prefetch_desc(&mapD);
     if (RTMA) {
       tma_prefetch_desc(&mapR);
-      for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
+      for (int i = 0; i < 2 * C::RDEPTH; ++i) mbar_init(&rfull_bar[i], 1);
     }
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -318,9 +319,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int half = (warp - 2) >> 2;   // 0: warps 2..5, 1: warps 6..9
     const int r = q * 32 + lane;
     const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(half * 2 * SUB_BYTES);  // this group's buffers
-    // RTMA: this group's two residual buffers (same 128 x 64 B, 64B-swizzled layout as the output buffers) + barriers
-    uint8_t* const rbuf = staging + C::OUT_STAGING_BYTES + half * 2 * SUB_BYTES;
-    uint64_t* const rfull = rfull_bar + half * 2;
+    // RTMA: this group's ring of residual buffers (same 128 x 64 B, 64B-swizzled layout as the output buffers) and
+    // their barriers; sub-tile number n (the group's running count `nstore`) lives in slot n % RD, phase (n / RD) & 1
+    constexpr uint32_t RD = C::RDEPTH;
+    uint8_t* const rbuf = staging + C::OUT_STAGING_BYTES + half * static_cast<int>(RD) * SUB_BYTES;
+    uint64_t* const rfull = rfull_bar + half * RD;
     const bool store_leader = q == 0 && lane == 0;
     const uint32_t row_off = static_cast<uint32_t>(r * SUBW * 2);
     const uint32_t swz = SUBW == 32 ? static_cast<uint32_t>((r >> 1) & 3) : 0u;  // 64B-swizzle XOR of the 16-byte chunk
@@ -476,16 +479,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // RTMA: the group's store leader requests residual sub-tile `sub` (index within this tile's share) into the
       // buffer the sub-tile counter selects; the TMA clips at row / image tails like the output store (zero fill)
       auto request_res = [&](int col0, int o0, int o1, int o2, uint32_t slot) {
-        uint8_t* dst = rbuf + (slot & 1u) * SUB_BYTES;
-        mbar_arrive_expect_tx(&rfull[slot & 1u], SUB_BYTES);
-        if (CONV) tma_load_4d(dst, &mapR, &rfull[slot & 1u], col0, o0, o1, o2);
-        else tma_load_3d(dst, &mapR, &rfull[slot & 1u], col0, o1, o0);
+        const uint32_t sl = slot % RD;
+        uint8_t* dst = rbuf + sl * SUB_BYTES;
+        mbar_arrive_expect_tx(&rfull[sl], SUB_BYTES);
+        if (CONV) tma_load_4d(dst, &mapR, &rfull[sl], col0, o0, o1, o2);
+        else tma_load_3d(dst, &mapR, &rfull[sl], col0, o1, o0);
       };
-      // the first two sub-tiles of a tile are requested at the end of the previous tile (below); only the very first
+      // the first RD sub-tiles of a tile are requested at the end of the previous tile (below); only the very first
       // tile of this CTA requests its own
       if (RTMA && store_leader && iter == 0) {
-        if (my_n > 0) request_res(obase + c_begin * 16, t0, t1, t2, nstore);
-        if (LG < my_n) request_res(obase + (c_begin + LG) * 16, t0, t1, t2, nstore + 1);
+#pragma unroll
+        for (uint32_t j = 0; j < RD; ++j)
+          if (static_cast<int>(j) * LG < my_n)
+            request_res(obase + (c_begin + static_cast<int>(j) * LG) * 16, t0, t1, t2, nstore + j);
       }
       if (my_n > 0) load_res(0);
 #pragma unroll
@@ -495,11 +501,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           V3D_ETRACE();  // group: TMEM data landed
           if ((g + 1) * LG < my_n) issue_group(g + 1, vb[(g + 1) & 1]);
           uint4 ca[LG][2], cb[LG][2];
-          if (RTMA) mbar_wait(&rfull[nstore & 1u], (nstore >> 1) & 1u);  // this sub-tile's residual rows have landed
+          if (RTMA) mbar_wait(&rfull[nstore % RD], (nstore / RD) & 1u);  // this sub-tile's residual rows have landed
 #pragma unroll
           for (int hh = 0; hh < LG; ++hh) {
             if (RTMA) {
-              const uint32_t rrow = smem_u32(rbuf) + (nstore & 1u) * SUB_BYTES + row_off;
+              const uint32_t rrow = smem_u32(rbuf) + (nstore % RD) * SUB_BYTES + row_off;
               ca[hh][0] = lds128(rrow + (((hh * 2) ^ swz) << 4));
               ca[hh][1] = lds128(rrow + (((hh * 2 + 1) ^ swz) << 4));
             } else {
@@ -646,10 +652,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   bulk_commit();
                 }
                 V3D_ETRACE();  // sub-tile handed to TMA
-                // RTMA: every thread of the group read this sub-tile's residual buffer before the barrier above, so
-                // the buffer can take the sub-tile after next
-                if (RTMA && store_leader && (g + 2) * LG < my_n)
-                  request_res(obase + (c_begin + (g + 2) * LG) * 16, t0, t1, t2, nstore);
+                // RTMA: every thread of the group read this sub-tile's residual slot before the barrier above, so
+                // the slot can take the sub-tile RD further on
+                if (RTMA && store_leader && (g + static_cast<int>(RD)) * LG < my_n)
+                  request_res(obase + (c_begin + (g + static_cast<int>(RD)) * LG) * 16, t0, t1, t2, nstore);
                 ++nstore;
               }
             }
@@ -657,15 +663,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       if (RTMA && store_leader && tile + static_cast<int>(gridDim.x) / NCTA < total_tiles) {
-        // both residual buffers are free now (every thread of the group passed the last sub-tile's barrier): request
+        // every residual slot is free now (every thread of the group passed the last sub-tile's barrier): request
         // the head of the NEXT tile's share, so that it is in shared memory before that tile's accumulator is ready
         int u0, u1, u2;
         tile_origin<CONV>(p, tw.m_tile * NCTA + cta_rank, u0, u1, u2);
         const int hsel_next = (NSUB & 1) ? (half ^ ((iter + 1) & 1)) : half;
         const int my_n_next = hsel_next ? NCH - CH_HALF : CH_HALF;
         const int col_next = tw.n_tile * OUT_COLS + c_begin_next * 16;
-        if (my_n_next > 0) request_res(col_next, u0, u1, u2, nstore);
-        if (LG < my_n_next) request_res(col_next + LG * 16, u0, u1, u2, nstore + 1);
+#pragma unroll
+        for (uint32_t j = 0; j < RD; ++j)
+          if (static_cast<int>(j) * LG < my_n_next)
+            request_res(col_next + static_cast<int>(j) * LG * 16, u0, u1, u2, nstore + j);
       }
       tc_fence_before();
       __syncwarp();
