@@ -100,6 +100,23 @@ def test_gemm_epilogue_full():
     assert_close(o32, F.silu(a.float() @ w.float().t() + bias), rtol=1e-3, atol=1e-3, what="epilogue fp32 silu")
 
 
+@pytest.mark.parametrize("N", [320, 256, 128, 64])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_gemm_single_residual_many_tiles(N, inplace):
+    """bf16 output + one residual over far more tiles than SMs (every CTA walks several tiles; N = 320 gives an odd
+    number of 32-column sub-tiles, so the two epilogue groups swap shares from tile to tile), residual separate or in
+    place (out is r1, the transformer's `t = t + f(t)` pattern), row tail included.  Also the case the opt-in epilogue
+    variants (CTA pairs, TMA-staged residual) are re-run on."""
+    M, K = 128 * 500 + 40, 64
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device=DEV)
+    r1 = rnd(M, N)
+    ref = 0.5 * (a.float() @ w.float().t() + bias) + 0.75 * r1.float()
+    out = r1.clone() if inplace else torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, K=K, N=N, rows_per_batch=M, bias=bias, r1=out if inplace else r1, s0=0.5, s1=0.75)
+    assert_close(out, ref, what=f"single residual N={N} inplace={inplace}")
+
+
 @pytest.mark.parametrize("n_out", [1280, 2560, 256])
 def test_gemm_geglu(n_out):
     M, K = 512, 320
