@@ -189,6 +189,23 @@ def test_conv3x3(n, h, w, c, co):
     assert_close(out, ref, what=f"conv3x3 {n}x{h}x{w}x{c}->{co}")
 
 
+@pytest.mark.parametrize("co", [320, 256])
+def test_conv3x3_residual_many_tiles(co):
+    """Implicit 3x3 conv + residual (the ResBlock's `conv(.) + skip`) over several tiles per CTA: 10 images of 64 x 64,
+    128-pixel boxes -> 320 pixel tiles x 2 (or 1) channel tiles; image tail (10 is not a multiple of what fits a box)."""
+    n, h, w, c = 10, 64, 64, 64
+    x = rnd(n, h, w, c)
+    wt = torch.randn(co, c, 3, 3, device=DEV) * (9 * c) ** -0.5
+    bias = torch.randn(co, device=DEV)
+    wp = bf(wt.permute(0, 2, 3, 1).reshape(co, 9 * c)).contiguous()
+    r1 = rnd(n * h * w, co)
+    out = torch.empty(n * h * w, co, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, wp, out, K=c, N=co, rows_per_batch=n * h * w, bias=bias, conv=(n, h, w), r1=r1, s1=1.0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), bf(wt).float(), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(n * h * w, co) + r1.float()
+    assert_close(out, ref, what=f"conv3x3 + residual, {co} channels, many tiles")
+
+
 def test_conv3x3_strided_input_and_residual():
     n, h, w, c, co, ld = 2, 32, 32, 64, 64, 192
     buf = rnd(n, h, w, ld)
