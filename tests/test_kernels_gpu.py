@@ -192,7 +192,7 @@ def test_conv3x3(n, h, w, c, co):
 @pytest.mark.parametrize("co", [320, 256])
 def test_conv3x3_residual_many_tiles(co):
     """Implicit 3x3 conv + residual (the ResBlock's `conv(.) + skip`) over several tiles per CTA: 10 images of 64 x 64,
-    128-pixel boxes -> 320 pixel tiles x 2 (or 1) channel tiles; image tail (10 is not a multiple of what fits a box)."""
+    64 x 2-pixel boxes -> 320 pixel tiles x 2 (or 1) channel tiles, i.e. 2-4 tiles per CTA."""
     n, h, w, c = 10, 64, 64, 64
     x = rnd(n, h, w, c)
     wt = torch.randn(co, c, 3, 3, device=DEV) * (9 * c) ** -0.5
