@@ -363,3 +363,25 @@ def test_bench_native_line_assembly():
     one = bench.assemble_line(args, sharded=True, **kw)
     assert one["scaling"] == "strong" and one["value"] == pytest.approx(18 * 3 / 4.5)
     assert one["e2e"]["d2h_bytes_per_step"] == 14155776 and "plan 'cfg'" in one["config"]["parallelism"]
+
+
+def test_schedule_cost_accounting_matches_known_flop_budget():
+    """tools/schedule_cost.py (meta-device dry run of the launch schedules): the algorithmic FLOPs it books for the
+    V3D_512 UNet forward and decode agree with the reference accounting of SURVEY.md App. B minus the documented
+    shortcuts (cross-attention over one token, cached positional embedding), and the sharding plans split the work."""
+    import importlib.util
+
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("schedule_cost", root / "tools" / "schedule_cost.py")
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    full = sc.run(18, 64, "none", 1, 0, 25)
+    tf = lambda book: sum(v[1] for v in book.values()) / 1e12          # noqa: E731
+    assert 43.0 < tf(full["unet_forward"]) < 45.68                       # 45.68 TF reference accounting, minus 1.94 TF
+    assert abs(tf(full["decode"]) - 54.77) < 0.5                         # decoder: nothing is skipped
+    assert full["unet_forward"]["gemm.conv3x3"][0] == 48 and full["unet_forward"]["groupnorm_apply"][0] == 105
+    cfg = sc.run(18, 64, "cfg", 2, 0, 25)
+    assert abs(tf(cfg["unet_forward"]) / tf(full["unet_forward"]) - 0.5) < 0.01
+    assert cfg["comm_per_unet_forward"]["cfg_gather"] == [1, 18 * 4 * 64 * 64 * 4]
+    views = sc.run(18, 64, "views", 2, 1, 25)
+    assert views["comm_per_unet_forward"]["halo"][0] == 44 and views["comm_per_unet_forward"]["kv_allgather"][0] == 16
