@@ -26,6 +26,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    # nvcc starts compressing the embedded cubin once it passes ~10 MB (the GEMM family does since the opt-in epilogue
+    # variants were added); keep the fat binary uncompressed, like every build that has run on the hardware so far
+    "--no-compress",
     "-I", str(INCLUDE), "-I", str(CSRC),
 ]
 # V3D_GEMM_DIAG=1 builds the GEMM with its diagnostics (role timelines, stage-skipping switches) compiled in
@@ -81,7 +84,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         objs = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
     newest = max(o.stat().st_mtime for o in objs)
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "--no-compress",
                "-o", str(LIB_PATH), *map(str, objs)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
