@@ -796,3 +796,34 @@ def test_views_from_image_matches_oracle_composition():
     print("views_from_image vs oracle composition: rel-L2", r, "cos", cs)
     assert frames.shape == ref.shape == (T, 3, side, side)
     assert r <= 5e-2 and cs >= 0.998
+
+
+@pytest.mark.parametrize("channel_mult,num_res_blocks,attention_resolutions", [
+    ((1, 2, 4), 1, (2, 1)),        # three levels, one block per level, no attention at the coarsest level
+    ((1, 1, 2, 2), 2, (4,)),       # repeated widths (no 1x1 skip convs in places), attention only at ds = 4
+])
+def test_unet_host_schedule_other_architectures_match_oracle(channel_mult, num_res_blocks, attention_resolutions):
+    """The execution plan is derived from the constructor arguments like the reference's loops
+    (video_model.py:186-440): other members of the SVD configuration family go through the same code and must agree
+    with the oracle built from the same arguments."""
+    import emu_ops
+    from oracle import ref_unet, synth
+    from v3d_b200.unet import VideoUNet
+
+    kw = dict(UNET_KW, channel_mult=list(channel_mult), num_res_blocks=num_res_blocks,
+              attention_resolutions=list(attention_resolutions))
+    net = VideoUNet(**kw)
+    sd = synth.synth_state_dict(net.param_shapes(), seed=17)
+    net.load_state_dict(sd, strict=True)
+    spec = ref_unet.UNetSpec(model_channels=64, channel_mult=channel_mult, num_res_blocks=num_res_blocks,
+                             attention_resolutions=attention_resolutions)
+    assert set(ref_unet.unet_param_shapes(spec)) == set(net.param_shapes())        # same state_dict keys
+    T, hw = 2, 16
+    xin, ts, ctx, y = _unet_inputs(T, hw)
+    with emu_ops.patched():
+        out = _run_unet(net.eval(), net._pack(torch.device("cpu")), xin, ts, ctx.reshape(2 * T, -1), y, T)
+    with torch.no_grad():
+        ref = ref_unet.unet_forward(sd, spec, xin, ts, ctx, y, T, torch.zeros(2, T))
+    r, cs = _rel(out, ref), _cos(out, ref)
+    print(channel_mult, num_res_blocks, attention_resolutions, "rel-L2", r, "cos", cs)
+    assert out.shape == ref.shape and r <= 3e-2 and cs >= 0.999
