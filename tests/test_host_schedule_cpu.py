@@ -827,3 +827,39 @@ def test_unet_host_schedule_other_architectures_match_oracle(channel_mult, num_r
     r, cs = _rel(out, ref), _cos(out, ref)
     print(channel_mult, num_res_blocks, attention_resolutions, "rel-L2", r, "cos", cs)
     assert out.shape == ref.shape and r <= 3e-2 and cs >= 0.999
+
+
+def test_decoder_and_encoder_other_architectures_match_oracle():
+    """Three-level, one-block-per-level first stage (ch_mult [1, 2, 4], num_res_blocks 1): decoder and encoder
+    schedules vs the oracle built from the same arguments."""
+    import emu_ops
+    from oracle import ref_decoder, ref_encoder, synth
+    from v3d_b200.decoder import VideoDecoder
+    from v3d_b200.encoder import Encoder
+
+    dec = VideoDecoder(**dict(DEC_KW, ch_mult=[1, 2, 4], num_res_blocks=1))
+    sd = synth.synth_state_dict(dec.param_shapes(), seed=19)
+    dec.load_state_dict(sd, strict=True)
+    spec = ref_decoder.DecoderSpec(ch=64, ch_mult=(1, 2, 4), num_res_blocks=1)
+    assert set(ref_decoder.decoder_param_shapes(spec)) == set(dec.param_shapes())
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(8))
+    with emu_ops.patched(), torch.no_grad():
+        out = dec.eval()._run(dec._pack(torch.device("cpu")), z, 2, 2, 1, 8, 8)
+        ref = ref_decoder.decoder_forward(sd, spec, z, 2)
+    r = _rel(out, ref)
+    print("decoder [1,2,4] x1: rel-L2", r)
+    assert out.shape == ref.shape == (2, 3, 32, 32) and r <= 3e-2 and _cos(out, ref) >= 0.999
+
+    enc = Encoder(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 4],
+                  num_res_blocks=1, attn_resolutions=[], dropout=0.0, attn_type="vanilla")
+    sde = synth.synth_state_dict(enc.param_shapes(), seed=20)
+    enc.load_state_dict(sde, strict=True)
+    espec = ref_encoder.EncoderSpec(ch=64, ch_mult=(1, 2, 4), num_res_blocks=1)
+    assert set(ref_encoder.encoder_param_shapes(espec)) == set(enc.param_shapes())
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    with emu_ops.patched(), torch.no_grad():
+        out = enc.eval()._run(enc._pack(torch.device("cpu")), x)
+        ref = ref_encoder.encoder_forward(sde, espec, x)
+    r = _rel(out, ref)
+    print("encoder [1,2,4] x1: rel-L2", r)
+    assert out.shape == ref.shape == (2, 8, 8, 8) and r <= 3e-2 and _cos(out, ref) >= 0.999
