@@ -53,6 +53,32 @@ def load_peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
+def csrc_digest() -> str:
+    """sha256 over the kernel sources: ties an ncu capture under profiles/ to the build it was taken from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "v3d_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    round's `ncu --set full` capture (profiles/traffic_r2.json, written by tools/ncu_summary.py).  DRAM counters cannot
+    be read outside a profiler, so the figure comes from that capture - and only while the kernel sources are the ones
+    it was taken from (`csrc_digest`); otherwise null."""
+    tpath = ROOT / "profiles" / "traffic_r2.json"
+    try:
+        d = json.loads(tpath.read_text())
+        if d.get("csrc_digest") != csrc_digest():
+            return None
+        return d
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
 
@@ -116,17 +142,27 @@ def _cpu_threads() -> int:
 class CpuReference:
     """Oracle port (oracle/, kind "port") of the reference path, fp32, on the host cores.
 
-    One `sample()` = one CFG-batched UNet forward (B = 2T, T frames) at TWO latent sizes + one first-stage decode of
-    T frames at TWO latent sizes.  The time at the full latent is the affine model  t(L) = a + b * L^2  through the
-    two measurements (a = per-forward fixed cost: ~2.4k small ops and 6 GB of fp32 weights; b = per-pixel cost), so the
-    fixed cost is not multiplied by the pixel ratio; the attention N^2 term is under-counted by this model, which
-    favours the CPU number.  The thread count is calibrated once (more threads than the box can really run make the
-    many small ops slower, not faster): `cores` in the JSON is the count actually used."""
+    mode "real-shape" (default whenever the CPU-time budget allows): one `sample()` runs, AT THE BENCHMARKED SHAPE
+    (latent 64 x 64, T frames), the network evaluation of ONE of the two CFG videos (B = T; [uc; c] are independent
+    batch items of every operator, so the CFG-batched forward costs twice this) and the first-stage decode of `nd`
+    whole frames (the decode's cost is linear in the frame count: the frames only meet in 3-tap temporal convolutions).
+        seconds per image = S * 2 * t_unet_half + (T / nd) * t_decode_nd
+    Nothing is extrapolated in resolution, so the N^2 attention term and the cache behaviour of the real tensors are in
+    the measurement.  The first sample of a run additionally times the full CFG-batched forward (B = 2T) once and
+    reports the ratio to 2 * t_unet_half as a check of the batch scaling.
 
-    # (UNet latents, decoder latents, cost of one sample in units of the calibration forward); V3D_512 itself is 64
+    mode "ladder" (fallback when K samples at the real shape do not fit the budget): round 1's two-size affine
+    extrapolation in the latent size.
+
+    The thread count is calibrated once (more threads than the box can really run make the many small ops slower,
+    not faster): `cores` in the JSON is the count actually used."""
+
     LADDER = (((16, 32), (8, 16), 20.0), ((8, 16), (4, 8), 5.5))
-    # all samples of a run (warm-up + timed) should fit in about this much CPU time (V3D_CPU_BUDGET_S overrides)
-    BUDGET_S = float(os.environ.get("V3D_CPU_BUDGET_S", "240"))
+    # all timed samples of a run should fit in about this much CPU time (V3D_CPU_BUDGET_S overrides)
+    BUDGET_S = float(os.environ.get("V3D_CPU_BUDGET_S", "900"))
+    # cost of the real-shape pieces in units of the calibration forward (latent 8, B = 2T), measured on two hosts;
+    # only used to decide what fits the budget
+    COST_UNET_HALF, COST_DEC_FRAME = 24.0, 5.0
 
     def __init__(self, T: int, S: int, latent: int, n_samples: int = 1):
         import torch
@@ -152,35 +188,52 @@ class CpuReference:
 
         self.sd_u = {k: rnd(s, k) for k, s in ref_unet.unet_param_shapes(self.spec_u).items()}
         self.sd_d = {k: rnd(s, k) for k, s in ref_decoder.decoder_param_shapes(self.spec_d).items()}
-        B = 2 * T
-        self.xin = {8: torch.randn(B, 8, 8, 8, generator=g)}
-        self.ts = torch.full((B,), 0.3)
-        self.ctx = torch.randn(B, 1, 1024, generator=g)
-        self.y = torch.randn(B, 768, generator=g)
-        self.ind = torch.zeros(2, T)
+        self.g = g
+        self.xin, self.z = {}, {}
         self.threads, self.thread_trials = self._calibrate_threads()
         torch.set_num_threads(self.threads)
-        # the largest sample sizes whose predicted cost fits the run's CPU-time budget
         t_cal = self.thread_trials[self.threads]
-        su, sdz = self.LADDER[-1][:2]
-        for lu, ldz, cost in self.LADDER:
-            if cost * t_cal * self.n_samples <= self.BUDGET_S:
-                su, sdz = lu, ldz
+        forced = os.environ.get("V3D_CPU_MODE")
+        per_sample = self.BUDGET_S / self.n_samples
+        self.nd = 0
+        for nd in (T, 6, 3, 2, 1):
+            if T % nd == 0 and (self.COST_UNET_HALF + nd * self.COST_DEC_FRAME) * t_cal <= per_sample:
+                self.nd = nd
                 break
-        self.su = tuple(min(x, latent) for x in su)
-        self.sdz = tuple(min(x, latent) for x in sdz)
-        for L in self.su:
-            self.xin.setdefault(L, torch.randn(B, 8, L, L, generator=g))
-        self.z = {L: torch.randn(T, 4, L, L, generator=g) for L in set(self.sdz)}
+        self.mode = forced or ("real-shape" if self.nd else "ladder")
+        if self.mode == "real-shape":
+            self.nd = self.nd or 1
+            self.full_forward_check = (self.COST_UNET_HALF * 3 + self.nd * self.COST_DEC_FRAME) * t_cal <= per_sample
+        else:
+            su, sdz = self.LADDER[-1][:2]
+            for lu, ldz, cost in self.LADDER:
+                if cost * t_cal * self.n_samples <= self.BUDGET_S:
+                    su, sdz = lu, ldz
+                    break
+            self.su = tuple(min(x, latent) for x in su)
+            self.sdz = tuple(min(x, latent) for x in sdz)
+        self.extra = {}
 
-    def _unet(self, L: int) -> float:
+    def _unet(self, L: int, videos: int = 2) -> float:
+        torch = self.torch
+        B = videos * self.T
+        key = (L, videos)
+        if key not in self.xin:
+            self.xin[key] = (torch.randn(B, 8, L, L, generator=self.g), torch.full((B,), 0.3),
+                             torch.randn(B, 1, 1024, generator=self.g), torch.randn(B, 768, generator=self.g),
+                             torch.zeros(videos, self.T))
+        x, ts, ctx, y, ind = self.xin[key]
         t0 = time.perf_counter()
-        self.ref_unet.unet_forward(self.sd_u, self.spec_u, self.xin[L], self.ts, self.ctx, self.y, self.T, self.ind)
+        self.ref_unet.unet_forward(self.sd_u, self.spec_u, x, ts, ctx, y, self.T, ind)
         return time.perf_counter() - t0
 
-    def _dec(self, L: int) -> float:
+    def _dec(self, L: int, frames: int = 0) -> float:
+        frames = frames or self.T
+        key = (L, frames)
+        if key not in self.z:
+            self.z[key] = self.torch.randn(frames, 4, L, L, generator=self.g)
         t0 = time.perf_counter()
-        self.ref_decoder.decoder_forward(self.sd_d, self.spec_d, self.z[L], self.T)
+        self.ref_decoder.decoder_forward(self.sd_d, self.spec_d, self.z[key], frames)
         return time.perf_counter() - t0
 
     def _calibrate_threads(self):
@@ -203,12 +256,27 @@ class CpuReference:
                     break
         return best_n, trials
 
-    def sample(self):
-        """-> (seconds of one UNet forward extrapolated to the full latent, seconds of the full decode), plus the
-        raw measurements in self.last"""
+    def warm(self):
+        """An untimed warm-up step: the cheap calibration forward (the real-shape pieces run for tens of seconds
+        each; their first-call costs - allocator growth, oneDNN primitive creation - are below 1 % of that)."""
         with self.torch.no_grad():
-            tu = [self._unet(L) for L in self.su]
-            td = [self._dec(L) for L in self.sdz]
+            self._unet(8)
+
+    def sample(self):
+        """-> (seconds of one CFG-batched UNet forward at the full size, seconds of the full decode); the raw
+        measurements in self.last"""
+        L = self.latent
+        with self.torch.no_grad():
+            if self.mode == "real-shape":
+                th = self._unet(L, videos=1)
+                tdn = self._dec(L, self.nd)
+                self.last = {"unet_half_batch_s": round(th, 3), f"decode_{self.nd}_frames_s": round(tdn, 3)}
+                if self.full_forward_check and "full_forward_s" not in self.extra:
+                    tf = self._unet(L, videos=2)
+                    self.extra = {"full_forward_s": round(tf, 3), "full_over_2x_half": round(tf / (2 * th), 3)}
+                return 2.0 * th, tdn * self.T / self.nd
+            tu = [self._unet(l) for l in self.su]
+            td = [self._dec(l) for l in self.sdz]
         self.last = {"unet_s": dict(zip(self.su, (round(t, 3) for t in tu))),
                      "decode_s": dict(zip(self.sdz, (round(t, 3) for t in td)))}
         return self._affine(self.su, tu), self._affine(self.sdz, td)
@@ -227,37 +295,49 @@ class CpuReference:
         return self.T / (self.S * t_unet_full + t_dec_full)
 
     def describe(self) -> str:
-        return (f"oracle port fp32, {self.threads} threads (calibrated over {sorted(self.thread_trials)}): per sample one "
-                f"CFG-batched UNet forward (B={2 * self.T}, T={self.T}) at latents {self.su[0]}^2 and {self.su[1]}^2 "
-                f"and one decode (T={self.T}) at latents {self.sdz[0]}^2 and {self.sdz[1]}^2; each extrapolated to "
-                f"latent {self.latent}^2 by the affine model t = a + b*pixels through its two sizes, UNet x {self.S} "
-                f"EDM steps (steps are cost-identical)")
+        head = f"oracle port fp32, {self.threads} threads (calibrated over {sorted(self.thread_trials)}), mode {self.mode}: "
+        if self.mode == "real-shape":
+            return head + (f"per sample, at the benchmarked shape (latent {self.latent}^2, T={self.T}): the network "
+                           f"evaluation of one of the two CFG videos (B={self.T}; x2 = the CFG-batched forward) and the "
+                           f"decode of {self.nd} of the {self.T} frames (x{self.T // self.nd}); image time = "
+                           f"{self.S} x 2 x t_unet_half + {self.T // self.nd} x t_decode; no extrapolation in resolution")
+        return head + (f"per sample one CFG-batched UNet forward (B={2 * self.T}, T={self.T}) at latents {self.su[0]}^2 and "
+                       f"{self.su[1]}^2 and one decode (T={self.T}) at latents {self.sdz[0]}^2 and {self.sdz[1]}^2; each "
+                       f"extrapolated to latent {self.latent}^2 by the affine model t = a + b*pixels through its two "
+                       f"sizes, UNet x {self.S} EDM steps (the CPU-time budget did not allow the real shape)")
+
+    def baseline_dict(self, value, tu, td) -> dict:
+        return {"value": value, "unit": "view-frames/s", "cores": self.threads, "kind": "port", "mode": self.mode,
+                "sample": self.describe(), "t_unet_forward_full_s": tu, "t_decode_full_s": td,
+                "last_sample_raw_s": self.last, "batch_scaling_check": self.extra or None,
+                "thread_calibration_s": self.thread_trials}
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref = CpuReference(args.frames, args.edm_steps, args.latent, n_samples=args.steps + args.warmup)
+    ref = CpuReference(args.frames, args.edm_steps, args.latent, n_samples=args.steps)
     for _ in range(args.warmup):
-        ref.sample()
-    tu = td = 0.0
+        ref.warm()
+    tus, tds = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         a, b = ref.sample()
-        tu += a
-        td += b
+        tus.append(a)
+        tds.append(b)
     wall = time.perf_counter() - t0
-    tu, td = tu / args.steps, td / args.steps
+    tu, td = sum(tus) / args.steps, sum(tds) / args.steps
     v = ref.frames_per_sec(tu, td)
+    base = ref.baseline_dict(v, tu, td)
+    base["per_sample_unet_forward_s"] = [round(x, 2) for x in tus]
+    base["per_sample_decode_s"] = [round(x, 2) for x in tds]
     line = {
         "impl": "reference", "metric": "view-frames/sec", "value": v, "unit": "view-frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "cpu"),
-        "cpu_baseline": {"value": v, "unit": "view-frames/s", "cores": ref.threads, "kind": "port",
-                         "sample": ref.describe(), "t_unet_forward_full_s": tu, "t_decode_full_s": td,
-                         "last_sample_raw_s": ref.last, "thread_calibration_s": ref.thread_trials},
+        "cpu_baseline": base,
         "e2e": {"value": v, "unit": "view-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -269,13 +349,12 @@ def workload_config(args, where: str) -> dict:
                         f"{args.edm_steps} Euler-EDM steps (CFG, B={2 * args.frames}) + first-stage decode; one image per GPU",
             "frames": args.frames, "edm_steps": args.edm_steps, "latent": [4, args.latent, args.latent],
             "cfg_scale": [args.min_cfg, args.max_cfg], "sigma_max": 700.0, "decode_chunk": args.frames,
-            "parallelism": ("host-cpu" if where == "cpu" else
-                            f"one image over {args.gpus} ranks, plan '{args.shard}' (views: frame blocks with K|V "
+            # the same dictionary in both arms (the reference arm runs the same workload on rank 0's host cores)
+            "parallelism": (f"one image over {args.gpus} ranks, plan '{args.shard}' (views: frame blocks with K|V "
                             "all-gather, conv halos, 3-D GN all-reduce; cfg: the CFG halves on a rank pair)"
                             if getattr(args, "shard", "images") != "images" else f"image-dp{args.gpus}"),
             "l2_policy": "working set per step (3 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush",
-            "weights": "random-init (seeded), zero-init modules re-randomised",
-            "cuda_graph": os.environ.get("V3D_CUDA_GRAPH", "1") != "0"}
+            "weights": "random-init (per-name seeded, oracle/synth.py), zero-init modules re-randomised"}
 
 
 def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d2h_bytes, sharded, probe_ms,
@@ -313,13 +392,7 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
             hbm_rows[fam] = {"launches": len(recs), "ms": round(fms, 3), "algorithmic_gb": round(gb, 2),
                              "achieved_gbs": round(gb / (fms * 1e-3), 1),
                              "frac_of_hbm_peak": round(gb / (fms * 1e-3) / peaks_hbm, 3)}
-    traffic = None
-    tpath = ROOT / "profiles" / "traffic_r1.json"
-    if tpath.exists():
-        try:
-            traffic = json.loads(tpath.read_text())
-        except Exception:
-            traffic = None
+    traffic = load_traffic()
     peak_tf = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"))
     n_img = 1 if sharded else world
     value = n_img * T * args.steps / secs
@@ -360,6 +433,72 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
 # ---------------------------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------------------------
+def load_synth_(module, dev, seed: int) -> None:
+    """Materialise the parameters of a module built under torch.device("meta") on `dev` with the per-name seeded
+    values of the parity fixtures (oracle/synth.py: a seeded generator, no reference arithmetic)."""
+    import torch
+    from oracle import synth
+
+    for name, p in list(module.named_parameters()):
+        val = synth.synth_tensor(name, tuple(p.shape), seed).to(dev)
+        mod = module
+        parts = name.split(".")
+        for part in parts[:-1]:
+            mod = mod._modules[part]
+        mod._parameters[parts[-1]] = torch.nn.Parameter(val, requires_grad=False)
+    module._invalidate()
+
+
+PARITY_TOL = {"rel_l2": 3e-2, "cosine": 0.999}   # DESIGN.md section 4 (bf16 path vs the fp32 reference)
+
+
+def parity_check(eng, dev, manifest) -> dict:
+    """Before anything is timed: ONE network evaluation and ONE decode at the benchmarked size (T = 18, latent 64 x 64,
+    CFG batch 36 / 18 frames -> 512 x 512) against the REAL reference's fp32 outputs on the same weights and inputs
+    (tests/golden/unet_v3d512.pt, decoder_v3d512.pt; oracle/make_golden.py).  Raises when out of tolerance."""
+    import torch
+    from oracle import synth
+
+    gold_dir = ROOT / "tests" / "golden"
+
+    def rel(a, b):
+        a, b = a.float(), b.float().to(a.device)
+        return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+    def cos(a, b):
+        a, b = a.float().flatten(), b.float().to(a.device).flatten()
+        return (a @ b / (a.norm() * b.norm()).clamp_min(1e-12)).item()
+
+    mu = manifest["unet_v3d512"]
+    T, hw = mu["T"], mu["latent_hw"]
+    gold = torch.load(gold_dir / "unet_v3d512.pt")
+    x, c, uc = synth.synth_inputs(T, hw, seed=mu["input_seed"])
+    xin = torch.cat([torch.cat([x, x]), torch.cat([uc["concat"], c["concat"]])], 1).to(dev)
+    ctx = torch.cat([uc["crossattn"], c["crossattn"]]).to(dev)
+    y = torch.cat([uc["vector"], c["vector"]]).to(dev)
+    with torch.no_grad():
+        out = eng.model.diffusion_model(xin, gold["timesteps"].to(dev), ctx, y, None, T,
+                                        torch.zeros(2, T, device=dev))
+    res = {"unet_forward": {"rel_l2": rel(out, gold["out"]), "cosine": cos(out, gold["out"]),
+                            "finite": bool(torch.isfinite(out).all()), "fixture": "tests/golden/unet_v3d512.pt"}}
+    md = manifest["decoder_v3d512"]
+    gold = torch.load(gold_dir / "decoder_v3d512.pt")
+    with torch.no_grad():
+        img = eng.first_stage_model.decoder(gold["z"].to(dev) / 0.18215, timesteps=md["T"])
+    st = gold["stride"]
+    res["decode"] = {"rel_l2": rel(img[:, :, ::st, ::st], gold["out_sub"]),
+                     "cosine": cos(img[:, :, ::st, ::st], gold["out_sub"]),
+                     "rel_l2_full_frames": rel(img[gold["full_frames"]], gold["out_full"]),
+                     "finite": bool(torch.isfinite(img).all()), "fixture": "tests/golden/decoder_v3d512.pt"}
+    res["tolerance"] = dict(PARITY_TOL)
+    res["against"] = "outputs of the real reference modules (fp32, CPU) on the same seeded weights and inputs"
+    for k in ("unet_forward", "decode"):
+        r = res[k]
+        if not (r["finite"] and r["rel_l2"] <= PARITY_TOL["rel_l2"] and r["cosine"] >= PARITY_TOL["cosine"]):
+            raise SystemExit(f"bench.py: parity check failed before timing: {k} {r}")
+    return res
+
+
 def run_native(args) -> None:
     import torch
 
@@ -391,9 +530,13 @@ def run_native(args) -> None:
             one = ViewShard(num_frames=T, rank=0, world=1)
             plan = ShardPlan("views", T, one, None, one)
     wrank = 0 if plan is not None else rank
-    eng.model.diffusion_model.init_random_(dev, seed=100 + wrank)
-    eng.first_stage_model.decoder.init_random_(dev, seed=200 + wrank)
+    # the weights of the parity fixtures (per-name seeded, bit-identical on every box and rank): the model that is
+    # timed below is the model that is checked against the real reference's outputs first
+    gold_manifest = json.loads((ROOT / "tests" / "golden" / "MANIFEST.json").read_text())
+    load_synth_(eng.model.diffusion_model, dev, gold_manifest["unet_v3d512"]["weight_seed"])
+    load_synth_(eng.first_stage_model.decoder, dev, gold_manifest["decoder_v3d512"]["weight_seed"])
     eng.eval()
+    parity = None if args.no_parity else parity_check(eng, dev, gold_manifest)
 
     # synthetic inputs in pinned host memory (one image per rank; the same image on every rank when view-sharded)
     g = torch.Generator().manual_seed(23 + wrank)
@@ -573,16 +716,18 @@ def run_native(args) -> None:
         membound={k: [(nb, ms(a, b)) for nb, a, b in v] for k, v in membound.items()},
         decode_families={k: [ms(a, b) for a, b in v] for k, v in decode_families.items()},
         decode_shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in decode_shapes.items()})
+    line["parity"] = parity
+    line["cuda_graph"] = os.environ.get("V3D_CUDA_GRAPH", "1") != "0"
     if plan is not None:
         line["shard_plan"] = dict(plan.describe(),
                                   cuda_graph_with_collectives=os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(T, S, L)
+        # bounded sample (about a minute of CPU work): one real-shape half-batch forward + a slice of the decode
+        os.environ.setdefault("V3D_CPU_BUDGET_S", "45")
+        CpuReference.BUDGET_S = float(os.environ["V3D_CPU_BUDGET_S"])
+        ref = CpuReference(T, S, L, n_samples=1)
         tu, td = ref.sample()
-        line["cpu_baseline"] = {"value": ref.frames_per_sec(tu, td), "unit": "view-frames/s", "cores": ref.threads,
-                                "kind": "port", "sample": ref.describe(), "t_unet_forward_full_s": tu,
-                                "t_decode_full_s": td, "last_sample_raw_s": ref.last,
-                                "thread_calibration_s": ref.thread_trials}
+        line["cpu_baseline"] = ref.baseline_dict(ref.frames_per_sec(tu, td), tu, td)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -601,6 +746,7 @@ def main():
     ap.add_argument("--min-cfg", type=float, default=3.5)
     ap.add_argument("--max-cfg", type=float, default=3.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against tests/golden")
     ap.add_argument("--shard", choices=["images", "views", "cfg", "cfg+views"], default="images",
                     help="images (default): one image per GPU, weak scaling.  ONE image over the GPUs (strong scaling): "
                          "views = frame blocks (K|V all-gather, conv halos, 3-D GroupNorm all-reduce); cfg = the [uc; c] "

@@ -33,7 +33,8 @@ def _pin(name: str, ref: torch.Tensor, ora: torch.Tensor) -> float:
     return err
 
 
-def _unet_case(ns, tag: str, model_channels: int, T: int, hw: int, wseed: int, sigma: float, manifest: dict):
+def _unet_case(ns, tag: str, model_channels: int, T: int, hw: int, wseed: int, sigma: float, manifest: dict,
+               tap_stride: int = 1):
     kw = dict(reference_shim.V3D_UNET_KW)
     kw["model_channels"] = model_channels
     net = ns.video_model.VideoUNet(**kw).eval()
@@ -69,11 +70,12 @@ def _unet_case(ns, tag: str, model_channels: int, T: int, hw: int, wseed: int, s
     blob = {"out": ref, "timesteps": ts}
     for w in want:
         # keep fixtures small: frames {0 (uc half), T (c half)}, every 8th channel, fp16
-        blob["tap:" + w] = taps_ref[w][[0, T]][:, ::8].half()
+        # (tap_stride > 1: also every tap_stride-th pixel -- the BASELINE-size fixture)
+        blob["tap:" + w] = taps_ref[w][[0, T]][:, ::8, ::tap_stride, ::tap_stride].half()
     torch.save(blob, OUT / f"{tag}.pt")
     manifest[tag] = dict(kind="unet_forward", model_channels=model_channels, T=T, latent_hw=hw, weight_seed=wseed,
                          input_seed=23, sigma=sigma, pin_err=err, ref_cpu_seconds=round(t_ref, 2),
-                         out_std=ref.std().item())
+                         out_std=ref.std().item(), tap_stride=tap_stride)
     return net, sd, spec
 
 
@@ -135,7 +137,8 @@ def _sampler_variant_case(ns, net, sd, spec, tag: str, T: int, hw: int, num_step
                          pin_err=err, out_std=ref.std().item())
 
 
-def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, manifest: dict, z=None):
+def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, manifest: dict, z=None,
+                  full_frames=None, stride: int = 1):
     kw = dict(reference_shim.V3D_DECODER_KW)
     kw["ch"] = ch
     dec = ns.temporal_ae.VideoDecoder(**kw).eval()
@@ -155,9 +158,16 @@ def _decoder_case(ns, tag: str, ch: int, T: int, B: int, hw: int, wseed: int, ma
         ora = ref_decoder.decode_first_stage(sd, spec, z, n_samples_a_time=T) if B == T else \
             ref_decoder.decoder_forward(sd, spec, z / 0.18215, T)
     err = _pin(tag, ref, ora)
-    torch.save({"out": ref, "z": z}, OUT / f"{tag}.pt")
+    if full_frames is None:
+        torch.save({"out": ref, "z": z}, OUT / f"{tag}.pt")
+    else:
+        # BASELINE-size fixture: `full_frames` complete frames + every stride-th pixel of all frames, fp16
+        # (the decoder output is an image in about [-1.5, 1.5]: fp16 rounding 5e-4 relative, far below the tolerance)
+        torch.save({"z": z, "full_frames": list(full_frames), "out_full": ref[list(full_frames)].half(),
+                    "stride": stride, "out_sub": ref[:, :, ::stride, ::stride].half()}, OUT / f"{tag}.pt")
     manifest[tag] = dict(kind="decode", ch=ch, T=T, B=B, latent_hw=hw, weight_seed=wseed, z_seed=77, pin_err=err,
-                         ref_cpu_seconds=round(t_ref, 2), out_std=ref.std().item())
+                         ref_cpu_seconds=round(t_ref, 2), out_std=ref.std().item(),
+                         full_frames=list(full_frames) if full_frames is not None else None, stride=stride)
 
 
 def _encoder_case(ns, tag: str, ch: int, B: int, hw: int, wseed: int, manifest: dict):
@@ -251,6 +261,18 @@ def main(argv):
         # BASELINE.json configs[0]: full-width VideoUNet, latent 4x32x32, T=4, 1 EDM step, fp32 CPU
         net, sd, spec = _unet_case(ns, "unet_full", 320, T=4, hw=32, wseed=3, sigma=3.0, manifest=manifest)
         _edm_step_case(ns, net, sd, spec, "edm_full_step", T=4, hw=32, num_steps=1, manifest=manifest)
+    if want("unet_v3d512"):
+        # BASELINE.json configs[1] network evaluation: full width, T=18, latent 64x64, CFG batch 36 (one forward)
+        _unet_case(ns, "unet_v3d512", 320, T=18, hw=64, wseed=3, sigma=3.0, manifest=manifest, tap_stride=4)
+    if want("edm_v3d512_25step"):
+        # 25 accumulating Euler-EDM steps (CFG, T=18) on the full-width network at the smallest latent that
+        # exercises every level (16x16 -> 2x2 at the bottom)
+        net, sd, spec = _unet_case(ns, "unet_full_t18_16", 320, T=18, hw=16, wseed=3, sigma=3.0, manifest=manifest)
+        _edm_step_case(ns, net, sd, spec, "edm_v3d512_25step", T=18, hw=16, num_steps=25, manifest=manifest)
+    if want("decoder_v3d512"):
+        # BASELINE.json configs[1] decode: 18 frames, latent 64x64 -> 512x512, one chunk
+        _decoder_case(ns, "decoder_v3d512", 128, T=18, B=18, hw=64, wseed=6, manifest=manifest,
+                      full_frames=(0, 11), stride=4)
     if want("decoder_small"):
         _decoder_case(ns, "decoder_small", 64, T=3, B=3, hw=16, wseed=4, manifest=manifest)
     if want("decoder_small_2videos"):

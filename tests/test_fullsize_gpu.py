@@ -9,8 +9,6 @@ decode to 512 x 512), where the oracle is far too slow to be the checker:
     the two videos of a batch; exercises 32-bit row / offset arithmetic at the largest shapes);
   * the frame-sharded path with world = 1 equals the dense path for a full UNet forward and a full decode.
 Random weights are generated on the device (init_random_), as in bench.py.
-First hardware run pending (written without GPU access): enabled with V3D_RUN_UNVALIDATED=1 and run that way, in a
-child process, by tests/test_zzz_first_run_gpu.py.
 """
 import os
 import sys
@@ -19,9 +17,7 @@ from pathlib import Path
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 ROOT = str(Path(__file__).resolve().parent.parent)
 sys.path.insert(0, ROOT)

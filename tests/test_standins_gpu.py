@@ -7,7 +7,6 @@ stand-ins there.
 Tolerance: bf16 outputs may differ by one rounding step where fp32 (kernel) and fp64 (stand-in) accumulation land on
 different sides of a tie -> |a - b| <= 2^-7 |b| + 2^-7 max|b| * 1e-2; fp32 outputs 2e-3 relative to the tensor scale
 (fast-math transcendentals: tanh.approx / ex2.approx).
-First hardware run pending (written without GPU access): V3D_RUN_UNVALIDATED=1, run by tests/test_zzz_first_run_gpu.py.
 """
 import os
 import sys
@@ -16,9 +15,7 @@ from pathlib import Path
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 DEV = "cuda"

@@ -18,11 +18,7 @@ from pathlib import Path
 import pytest
 import torch
 
-# first hardware run pending (written after the round-1 GPU budget was spent): enabled with V3D_RUN_UNVALIDATED=1;
-# tests/test_zzz_first_run_gpu.py runs this file that way in a child process at the end of the GPU suite
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 ROOT = str(Path(__file__).resolve().parent.parent)
 DEV = "cuda"

@@ -23,15 +23,8 @@ OUT = TESTS.parent / "gpurun_out"
 # group -> (pytest selection, timeout in seconds).  Kept light: the whole file adds a few minutes to the GPU suite; the
 # 4-process composite plan and the NCCL variants are run by hand (tools/gpu_round.sh).
 GROUPS = {
-    "kernels": ([str(TESTS / "test_kernels_gpu.py"), "-k", "heun_step_kernel or concat_timestep_embedder"], 300),
-    "attention_poly_exp2": ([str(TESTS / "test_kernels_gpu.py"), "-k", "attention_poly_exp2"], 600),
-    "parity": ([str(TESTS / "test_parity_gpu.py"), "-k", "encoder or heun or vanilla or central"], 600),
-    "viewshard_kernels": ([str(TESTS / "test_viewshard_gpu.py"), "-k", "halo_mode or split_kv"], 300),
-    "viewshard_engine": ([str(TESTS / "test_viewshard_gpu.py"), "-k",
-                          "single_rank or view_sharded_engine_matches_unsharded_one_gpu_gloo or "
-                          "cfg_split_engine_matches_unsharded_one_gpu_gloo"], 600),
-    "fullsize_properties": ([str(TESTS / "test_fullsize_gpu.py")], 600),
-    "kernels_vs_standins": ([str(TESTS / "test_standins_gpu.py")], 300),
+    "gemm_tma_staged_residual": ([str(TESTS / "test_kernels_gpu.py"), "-k", "tma_staged_residual"], 600),
+    "gemm_cta_pair": ([str(TESTS / "test_kernels_gpu.py"), "-k", "cta_pair"], 600),
 }
 
 

@@ -60,7 +60,7 @@ for stage in "$@"; do
       for k in 0 1 2 3; do V3D_ATTN_POLY=$k run 300 "micro_attn_poly$k.log" $PY tools/microbench.py attn; done ;;
     bench)
       run 900 bench.json $PY bench.py --steps 3 --warmup 3
-      run 900 bench_ref.json $PY bench.py --impl reference --steps 1 --warmup 1 ;;
+      run 900 bench_ref.json $PY bench.py --impl reference --steps 2 --warmup 1 ;;
     sweep)
       run 1500 sweep.log $PY tools/sweep.py ;;
     bench_pair)
@@ -73,6 +73,12 @@ for stage in "$@"; do
         V3D_CUDA_GRAPH=0 run 600 "ncu_full_$k.log" ncu --set full --clock-control none --import-source on \
           -k "regex:$k" -s 40 -c 3 -o "gpurun_out/full_$k" -f $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline
       done ;;
+    ncu_set)
+      # ONE ncu --set full run over every kernel family at its V3D_512 top-level shape (tools/microbench.py ncu_set)
+      run 900 ncu_set.log ncu --set full --clock-control none --import-source on \
+        -k "regex:gn_|layernorm|attn_|gemm_tc|softmax_rows" -c 40 -o gpurun_out/ncu_set -f $PY tools/microbench.py ncu_set ;;
+    micro_all)
+      run 600 micro_all.log $PY tools/microbench.py gemm conv attn norm small ;;
     viewshard2)
       V3D_RUN_UNVALIDATED=1 run 600 viewshard_nccl.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "nccl"
       run 900 bench_views2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \

@@ -213,6 +213,37 @@ if __name__ == "__main__":
         if ntile > 12:
             print("steady-state cycles per tile (epilogue):", (E[per * (ntile - 2)] - E[per * 8]) / (ntile - 2 - 8))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu_set":
+        # one process, two launches of every kernel family at its V3D_512 top-level shape: the target of ONE
+        # `ncu --set full -k regex:"gn_|layernorm|attn_|gemm_tc|softmax_rows"` run (profiles/: one capture per kernel)
+        ns, rows, c = 36, 4096, 320
+        x = bf(ns * rows, c)
+        y = torch.empty_like(x)
+        g, b = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+        st = torch.zeros(ns, 32, 2, device=DEV, dtype=torch.float64)
+        qkv = bf(ns * rows, 3 * c)
+        o = torch.empty(ns * rows, c, device=DEV, dtype=torch.bfloat16)
+        wt = bf(c, 9 * c, scale=(9 * c) ** -0.5)
+        wl = bf(c, c, scale=c ** -0.5)
+        wg = bf(8 * c, c, scale=c ** -0.5)
+        og = torch.empty(ns * rows, 4 * c, device=DEV, dtype=torch.bfloat16)
+        bias, bias8 = torch.randn(c, device=DEV), torch.randn(8 * c, device=DEV)
+        sc = torch.randn(4 * 4096, 4096, device=DEV)
+        pr = torch.empty(4 * 4096, 4096, device=DEV, dtype=torch.bfloat16)
+        for _ in range(2):
+            ops.groupnorm_stats(x, st, rows, ns, c)
+            ops.groupnorm_apply(x, y, st, g, b, rows, ns, c, 1e-5, True)
+            ops.groupnorm_stats(x, st[:2], 18 * rows, 2, c)
+            ops.groupnorm_apply(x, y, st[:2], g, b, 18 * rows, 2, c, 1e-5, True)
+            ops.layernorm(x, y, g, b, ns * rows, c)
+            ops.attention_temporal(qkv, o, 2, 18, rows, 5, 0.125)
+            ops.attention_spatial(qkv, o, ns, rows, 5, 0.125)
+            ops.gemm(x, wt, o, K=c, N=c, rows_per_batch=ns * rows, bias=bias, conv=(ns, 64, 64))
+            ops.gemm(x, wl, o, K=c, N=c, rows_per_batch=ns * rows, bias=bias, r1=y, s1=1.0)
+            ops.gemm(x, wg, og, K=c, N=8 * c, rows_per_batch=ns * rows, bias=bias8, act=ops.ACT_GEGLU)
+            ops.softmax_rows_f32(sc, pr, 4 * 4096, 4096)
+        torch.cuda.synchronize()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one_conv":
         n, h, w, ci, co = 36, 64, 64, 320, 320
         x, wt = bf(n * h * w, ci), bf(co, 9 * ci, scale=(9 * ci) ** -0.5)

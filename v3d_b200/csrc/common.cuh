@@ -413,8 +413,11 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 // max |deviation from x * Phi(x)| = 2.5e-5 (the usual "tanh GELU" constants give 4.7e-4), plus tanh.approx's
 // 2^-11 relative error.  8 FP32 ops + 1 MUFU per element instead of ~24 for a direct erf evaluation, which
 // matters because the GEGLU GEMM epilogue is issue-bound at K = 320.
+// P is only meaningful inside the fitted range (it turns negative beyond |x| ~ 11.1, which would flip the tanh): x^2 is
+// clamped to 64 before the polynomial, so for |x| > 8 the argument is x * P(64) = 1.73 x, |.| > 13.8, tanh = +-1 and
+// Phi is exactly 0 / 1 as in fp32 erf.
 __device__ __forceinline__ float gelu_phi_fast(float x) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, 64.0f);
   float p = fmaf(x2, -0.00035151753388801277f, 0.03700565095560008f);
   p = fmaf(x2, p, 0.7975078784258718f);
   return fmaf(tanh_approx(x * p), 0.5f, 0.5f);  // Phi(x)
@@ -422,7 +425,9 @@ __device__ __forceinline__ float gelu_phi_fast(float x) {
 __device__ __forceinline__ float gelu_erf_fast(float x) { return x * gelu_phi_fast(x); }
 // the same function on a packed pair: 6 packed FP32 ops + 2 MUFU for two elements
 __device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x) {
-  const uint64_t xx = mul2(x, x);
+  float xa, xb;
+  unpack2(mul2(x, x), xa, xb);
+  const uint64_t xx = pack2(fminf(xa, 64.0f), fminf(xb, 64.0f));  // range guard, see gelu_phi_fast
   uint64_t p = fma2(xx, pack2(-0.00035151753388801277f, -0.00035151753388801277f),
                     pack2(0.03700565095560008f, 0.03700565095560008f));
   p = fma2(xx, p, pack2(0.7975078784258718f, 0.7975078784258718f));
