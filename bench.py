@@ -499,6 +499,128 @@ def parity_check(eng, dev, manifest) -> dict:
     return res
 
 
+def probe_exchanges(plan):
+    """Bracket every exchange of a one-image-over-ranks plan with CUDA events (eager step only).
+    -> ({kind: [(e0, e1)]}, restore())"""
+    import torch
+
+    events, saved = {}, []
+    if plan is None:
+        return events, lambda: None
+    targets = []
+    for obj, prefix in ((plan.sample, ""), (plan.decode if plan.decode is not plan.sample else None, "decode_"),
+                        (plan.cfg, "")):
+        if obj is None:
+            continue
+        for meth, kind in (("allreduce_stats_", "gn_allreduce"), ("exchange_halos", "halo"), ("gather_rows", "kv_allgather"),
+                           ("gather_frames", "frame_gather"), ("gather_halves", "cfg_gather")):
+            if hasattr(obj, meth):
+                targets.append((obj, meth, prefix + kind))
+    for obj, meth, kind in targets:
+        fn = getattr(obj, meth)
+
+        def wrapped(*a, _fn=fn, _kind=kind, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = _fn(*a, **kw)
+            e1.record()
+            events.setdefault(_kind, []).append((e0, e1))
+            return r
+
+        saved.append((obj, meth))
+        setattr(obj, meth, wrapped)
+
+    def restore():
+        for obj, meth in saved:
+            try:
+                delattr(obj, meth)      # instance attribute shadowing the class's method
+            except AttributeError:
+                pass
+
+    return events, restore
+
+
+def summarise_exchanges(events, probe_ms: float) -> dict:
+    """Per-kind device time of the exchanges of one eager step (CUDA events on the launching stream around each
+    torch.distributed call: transfer + the wait for the slowest peer, i.e. load imbalance shows up here)."""
+    out = {}
+    for kind, evs in sorted(events.items()):
+        t = sum(a.elapsed_time(b) for a, b in evs)
+        out[kind] = {"calls": len(evs), "ms": round(t, 3)}
+    tot = sum(v["ms"] for v in out.values())
+    out["_all_exchanges_ms"] = round(tot, 3)
+    out["_eager_probed_step_ms"] = round(probe_ms, 3)
+    out["_share_of_step"] = round(tot / probe_ms, 4) if probe_ms > 0 else None
+    if out and tot > 0:
+        out["_limiting"] = max((k for k in out if not k.startswith("_")), key=lambda k: out[k]["ms"])
+    return out
+
+
+def measure_strong(args, eng, dev, rank, world, T, L) -> dict:
+    """ONE image over the N ranks (BASELINE.json north_star: the T view-frames sharded over the GPUs of a box with the
+    temporal-attention K|V all-gather, plus the CFG-pair split of SURVEY.md 8(e)); every plan that fits N is timed
+    (same weights and the same image on every rank, device-resident inputs, CUDA events, max over ranks)."""
+    import torch
+
+    from v3d_b200 import ops, parallel
+    from v3d_b200.viewshard import ShardPlan
+
+    modes = [m for m in (os.environ.get("V3D_STRONG_PLANS", "views,cfg,cfg+views").split(","))
+             if (m == "views" and world <= T) or (m == "cfg" and world == 2) or
+             (m == "cfg+views" and world >= 4 and world % 2 == 0 and T // (world // 2) >= 2)]
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(T, 4, L, L, generator=g).to(dev)
+    c = {"crossattn": torch.randn(1, 1, 1024, generator=g).repeat(T, 1, 1).to(dev),
+         "concat": torch.randn(1, 4, L, L, generator=g).repeat(T, 1, 1, 1).to(dev),
+         "vector": torch.randn(T, 768, generator=g).to(dev)}
+    uc = {"crossattn": torch.zeros_like(c["crossattn"]), "concat": torch.zeros_like(c["concat"]), "vector": c["vector"].clone()}
+    k = max(1, min(args.steps, 2))
+    out = {"steps": k, "warmup": 1, "unit": "view-frames/s", "plans": {},
+           "note": "one image (T view-frames) over all ranks; value = T * steps / max-over-ranks seconds"}
+    for mode in modes:
+        plan = ShardPlan.create(T, mode)
+
+        def step():
+            img = eng.sample_views(x.clone(), c, uc, num_frames=T, decoding_t=T, shard=plan)
+            u8 = torch.empty(img.shape[0], 8 * L, 8 * L, 3, device=dev, dtype=torch.uint8)
+            ops.frames_nchw_to_u8(img.contiguous(), u8)
+            return plan.gather_frames(u8)
+
+        step()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        secs = parallel.max_over_ranks(e0.elapsed_time(e1) / 1000.0, dev)
+        # one more step with events around every exchange (rank 0's view)
+        events, restore = probe_exchanges(plan)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        unet = eng.model.diffusion_model
+        graphs_were, unet.cuda_graphs = unet.cuda_graphs, False   # eager: the events sit between individual launches
+        try:
+            p0.record()
+            step()
+            p1.record()
+            torch.cuda.synchronize()
+        finally:
+            unet.cuda_graphs = graphs_were
+            restore()
+        out["plans"][mode] = {"value": T * k / secs, "ms_per_image": 1000.0 * secs / k,
+                              "blocks": plan.describe().get("sample_blocks") or plan.describe().get("decode_blocks"),
+                              "exchanges_ms_per_image": summarise_exchanges(events, p0.elapsed_time(p1))}
+    if out["plans"]:
+        best = max(out["plans"], key=lambda m: out["plans"][m]["value"])
+        out["best_plan"] = best
+        out["value"] = out["plans"][best]["value"]
+        out["ms_per_image"] = out["plans"][best]["ms_per_image"]
+    return out
+
+
 def run_native(args) -> None:
     import torch
 
@@ -663,6 +785,8 @@ def run_native(args) -> None:
                     nbytes = 2 * a[2] * a[3] * a[4]
                 elif name == "groupnorm_apply":        # (x, y, stats, gamma, beta, rows_per_sample, nsamples, c)
                     nbytes = 2 * 2 * a[5] * a[6] * a[7]
+                elif name == "groupnorm":              # one launch (x, y, gamma, beta, rows_per_sample, nsamples, c):
+                    nbytes = 2 * 2 * a[4] * a[5] * a[6]    # x read once from HBM (re-read from L2), y written
                 elif name == "layernorm":              # (x, y, gamma, beta, rows, c): read + write (+ the fused sum)
                     nbytes = 2 * (3 if kw.get("ysum") is not None else 2) * a[4] * a[5]
                 elif name == "attention_temporal":     # (qkv, out, nb, t, s, nheads): q, k, v read, o written
@@ -679,6 +803,7 @@ def run_native(args) -> None:
         if callable(fn) and not name.startswith("_") and name not in host_only and getattr(fn, "__module__", "") == ops.__name__:
             saved[name] = fn
             setattr(ops, name, make_probe(name, fn))
+    xchg_events, xchg_restore = probe_exchanges(plan)
     unet = eng.model.diffusion_model
     graphs_were = unet.cuda_graphs
     unet.cuda_graphs = False  # the probe needs eager launches (events between individual kernels)
@@ -702,6 +827,7 @@ def run_native(args) -> None:
         torch.cuda.synchronize()
     finally:
         unet.cuda_graphs = graphs_were
+        xchg_restore()
         del first_stage.decode          # back to the class's method
         for name, fn in saved.items():
             setattr(ops, name, fn)
@@ -717,6 +843,11 @@ def run_native(args) -> None:
         decode_families={k: [ms(a, b) for a, b in v] for k, v in decode_families.items()},
         decode_shapes={k: [(f, ms(a, b)) for f, a, b in v] for k, v in decode_shapes.items()})
     line["parity"] = parity
+    if plan is not None:
+        line["exchanges_ms_per_step"] = summarise_exchanges(xchg_events, ms(pe0, pe1))
+    elif world > 1 and not args.no_strong:
+        # BASELINE.json's north_star split next to the image-parallel throughput: ONE image over the N GPUs
+        line["strong"] = measure_strong(args, eng, dev, rank, world, T, L)
     line["cuda_graph"] = os.environ.get("V3D_CUDA_GRAPH", "1") != "0"
     if plan is not None:
         line["shard_plan"] = dict(plan.describe(),
@@ -746,6 +877,8 @@ def main():
     ap.add_argument("--min-cfg", type=float, default=3.5)
     ap.add_argument("--max-cfg", type=float, default=3.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="N > 1, image-parallel run: skip the one-image-over-N-GPUs sub-measurement (`strong`)")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against tests/golden")
     ap.add_argument("--shard", choices=["images", "views", "cfg", "cfg+views"], default="images",
                     help="images (default): one image per GPU, weak scaling.  ONE image over the GPUs (strong scaling): "

@@ -119,6 +119,15 @@ int v3d_groupnorm_stats(const void* x, void* stats, int64_t rows_per_sample, int
 int v3d_groupnorm_apply(const void* x, void* y, const void* stats, const void* gamma, const void* beta,
                         int64_t rows_per_sample, int32_t nsamples, int32_t C, int32_t ldx, int32_t groups,
                         float eps, int32_t silu, void* stream);
+/* The same normalisation in ONE launch (statistics -> grid-wide barrier -> apply): what the unsharded path calls;
+ * the pair above remains for the frame-sharded path, where the statistics are all-reduced between the two passes.
+ * Deterministic (per-CTA fp32 partials folded by warp-shuffle trees, summed in fp64 in a fixed order; no atomics on
+ * data).  `workspace`: >= v3d_groupnorm_workspace_bytes() bytes of device memory, zeroed once by the caller and then
+ * passed unchanged to every call issued on the same stream (it holds the barrier state and the partials). */
+int64_t v3d_groupnorm_workspace_bytes(void);
+int v3d_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows_per_sample,
+                  int32_t nsamples, int32_t C, int32_t ldx, int32_t groups, float eps, int32_t silu,
+                  void* workspace, int64_t workspace_bytes, void* stream);
 /* LayerNorm over C (attention.py:525-527; video_attention.py:51,79,93-94). Optional fused
  * z = x + add[row / rows_per_frame] (fp32 vectors; video_attention.py:286-287), z stored to ysum. */
 int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const void* gamma, const void* beta,

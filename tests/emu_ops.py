@@ -126,6 +126,19 @@ def groupnorm_stats(x, stats, rows_per_sample, nsamples, c, ldx=None, groups=32,
     return stats
 
 
+def groupnorm_workspace(device):
+    return torch.zeros(8, dtype=torch.uint8)
+
+
+def groupnorm(x, y, gamma, beta, rows_per_sample, nsamples, c, eps, silu, workspace, ldx=None, groups=32):
+    """single-launch GroupNorm = statistics + apply (one tick: one launch)"""
+    st = torch.zeros(nsamples, groups, 2, dtype=torch.float64)
+    groupnorm_stats(x, st, rows_per_sample, nsamples, c, ldx=ldx, groups=groups, pre_zeroed=True)
+    groupnorm_apply(x, y, st, gamma, beta, rows_per_sample, nsamples, c, eps, silu, ldx=ldx, groups=groups)
+    _tick(-1)
+    return y
+
+
 def groupnorm_apply(x, y, stats, gamma, beta, rows_per_sample, nsamples, c, eps, silu, ldx=None, groups=32):
     _tick()
     ldx = c if ldx is None else ldx
@@ -345,7 +358,7 @@ def frames_nchw_to_u8(x, y):
     return y
 
 
-_EMULATED = ["launch_count", "gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "softmax_rows_f32",
+_EMULATED = ["launch_count", "gemm", "groupnorm_stats", "groupnorm_apply", "groupnorm", "groupnorm_workspace", "layernorm", "softmax_rows_f32",
              "attention_spatial", "attention_temporal", "attention_temporal_kv", "upsample_nearest2x", "copy_channels",
              "im2col3x3", "nchw_f32_to_nhwc_bf16", "nhwc_to_nchw_f32", "small_linear", "timestep_embedding",
              "time_mix_conv", "edm_scale_input", "edm_denoise_combine", "cfg_combine", "euler_step", "heun_step",

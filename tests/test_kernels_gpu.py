@@ -262,6 +262,37 @@ def test_groupnorm(ns, rows, c, eps, silu):
     if silu:
         ref = F.silu(ref)
     assert_close(y, ref, what="groupnorm")
+    # the single-launch form (statistics -> grid barrier -> apply): same contract, and bit-reproducible
+    ws = ops.groupnorm_workspace(DEV)
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    ops.groupnorm(x, y1, gamma, beta, rows, ns, c, eps, silu, ws)
+    assert_close(y1, ref, what="groupnorm (one launch)")
+    for _ in range(3):      # back-to-back launches share the barrier words: the sense reversal must hold
+        ops.groupnorm(x, y2, gamma, beta, rows, ns, c, eps, silu, ws)
+    assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("ns,rows,c", [(36, 4096, 320), (2, 18 * 4096, 320), (36, 64, 1280), (18, 16384, 128),
+                                       (36, 1024, 1920), (1, 18 * 1024, 640)])
+def test_groupnorm_one_launch_model_shapes(ns, rows, c):
+    """V3D_512 shapes (2-D per-frame and 3-D time_stack norms, skip-concat widths, a strided input view) through the
+    single-launch kernel against the statistics + apply pair; the two must agree to the rounding of the output."""
+    x = bf(torch.randn(ns * rows, c, device=DEV) * 1.5 + 0.25)
+    gamma, beta = torch.randn(c, device=DEV), torch.randn(c, device=DEV)
+    stats = torch.empty(ns, 32, 2, device=DEV, dtype=torch.float64)
+    y0, y1 = torch.empty_like(x), torch.empty_like(x)
+    ops.groupnorm_stats(x, stats, rows, ns, c)
+    ops.groupnorm_apply(x, y0, stats, gamma, beta, rows, ns, c, 1e-5, True)
+    ws = ops.groupnorm_workspace(DEV)
+    ops.groupnorm(x, y1, gamma, beta, rows, ns, c, 1e-5, True, ws)
+    assert_close(y1, y0, rtol=1.0 / 128, atol=1e-2, what="one-launch vs pair")
+    # strided input (a column slice of a wider matrix), dense output
+    wide = bf(torch.randn(ns * rows, c + 64, device=DEV))
+    xs = wide[:, 64:]
+    y2, y3 = torch.empty_like(x), torch.empty_like(x)
+    ops.groupnorm(xs, y2, gamma, beta, rows, ns, c, 1e-5, False, ws, ldx=c + 64)
+    ops.groupnorm(xs.contiguous(), y3, gamma, beta, rows, ns, c, 1e-5, False, ws)
+    assert torch.equal(y2, y3)
 
 
 @pytest.mark.parametrize("rows,c,rpf", [(4096, 320, 1024), (777, 1280, 7), (128, 64, 128), (300, 640, 100)])

@@ -121,6 +121,12 @@ def test_groupnorm_and_layernorm(silu):
     o1, o2 = both("groupnorm_apply", lambda: torch.empty(ns * rows, c, device=DEV, dtype=torch.bfloat16), x, OUT, s2, g,
                   b, rows, ns, c, 1e-5, silu)
     close(o1, o2, "groupnorm apply")
+    y1 = torch.empty(ns * rows, c, device=DEV, dtype=torch.bfloat16)
+    y2 = torch.empty_like(y1)
+    ops.groupnorm(x, y1, g, b, rows, ns, c, 1e-5, silu, ops.groupnorm_workspace(DEV))
+    emu.groupnorm(x, y2, g, b, rows, ns, c, 1e-5, silu, None)
+    torch.cuda.synchronize()
+    close(y1, y2, "groupnorm (one launch)")
     add = f32(ns, c, seed=4)
     ys1 = torch.empty(ns * rows, c, device=DEV, dtype=torch.bfloat16)
     ys2 = torch.empty_like(ys1)

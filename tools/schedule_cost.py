@@ -62,6 +62,16 @@ def groupnorm_stats(x, stats, rows_per_sample, nsamples, c, **kw):
     return stats
 
 
+def groupnorm_workspace(device):
+    return None
+
+
+def groupnorm(x, y, gamma, beta, rows_per_sample, nsamples, c, eps, silu, workspace, **kw):
+    # one launch: x read (HBM), re-read (L2 when it fits), y written -- algorithmic bytes = read once + write once
+    book("groupnorm", 0, 2 * rows_per_sample * nsamples * c * 2)
+    return y
+
+
 def groupnorm_apply(x, y, stats, gamma, beta, rows_per_sample, nsamples, c, eps, silu, **kw):
     book("groupnorm_apply", 0, 2 * rows_per_sample * nsamples * c * 2)
     return y
@@ -132,7 +142,7 @@ def time_mix_conv(x, ldx, w, bias, y, nb, t, hw, c):
     return y
 
 
-COUNTERS = ["gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "softmax_rows_f32", "attention_spatial",
+COUNTERS = ["gemm", "groupnorm_stats", "groupnorm_apply", "groupnorm", "groupnorm_workspace", "layernorm", "softmax_rows_f32", "attention_spatial",
             "attention_temporal", "attention_temporal_kv", "upsample_nearest2x", "copy_channels", "im2col3x3",
             "nchw_f32_to_nhwc_bf16", "nhwc_to_nchw_f32", "small_linear", "timestep_embedding", "time_mix_conv"]
 

@@ -1047,17 +1047,27 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       e.b_batched = 1;
     }
   }
-  // CTA-pair (cta_group::2) tiles: opt-in (V3D_GEMM_2CTA=1) until validated on hardware; wide bf16-output tiles only
+  // CTA-pair (cta_group::2) tiles, wide bf16-output tiles only.  V3D_GEMM_2CTA: unset / "auto" = per-shape choice
+  // from the round-2 hardware timings (profiles/microbench_r2_pair_rtma.md: +5..8 % on the 256-wide GEGLU and decoder
+  // conv tiles, +12 % on the decoder's 128-wide top level, +2..3 % on the residual-free projections; temporal convs,
+  // residual epilogues and short grids lose), "1" = every eligible tile, "0" = never.
   bool pair = false;
   {
-    static int want_pair = -1;
-    if (want_pair < 0) {
+    static int want_pair = -2;
+    if (want_pair == -2) {
       const char* v = getenv("V3D_GEMM_2CTA");
-      want_pair = (v && atoi(v) != 0) ? 1 : 0;
+      want_pair = (v == nullptr || v[0] == 'a') ? -1 : (atoi(v) != 0 ? 1 : 0);
     }
     const bool staged_out = !a->out_transposed && !a->out_fp32;
-    pair = want_pair == 1 && staged_out && e.num_m_tiles >= 2 &&
-           (bn == 256 || ((bn == 160 || bn == 128) && a->act != V3D_ACT_GEGLU));  // 128: the decoder's top levels
+    const bool eligible = staged_out && e.num_m_tiles >= 2 &&
+                          (bn == 256 || ((bn == 160 || bn == 128) && a->act != V3D_ACT_GEGLU));
+    if (want_pair == 1) {
+      pair = eligible;
+    } else if (want_pair == -1 && eligible && a->R1 == nullptr && a->R2 == nullptr) {
+      if (a->act == V3D_ACT_GEGLU) pair = e.num_m_tiles >= 16;
+      else if (conv) pair = e.num_m_tiles >= 64 && (bn != 160 || a->K >= 640);
+      else if (ntaps == 1) pair = e.num_m_tiles >= 64 && b_batch == 1;
+    }
   }
   {
     const uint64_t ktot = (uint64_t)ntaps * a->K;
@@ -1084,16 +1094,19 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
     e.R2 = nullptr;
   }
   if (epi_kind == EPI_BF16 && e.R2 != nullptr) epi_kind = EPI_BF16R2;
-  // TMA-staged residual: opt-in (V3D_GEMM_RTMA=1) until timed on hardware; single residual, 32-column sub-tiles, one CTA
+  // TMA-staged residual (EPI_BF16RT): single residual, 32-column sub-tiles, one CTA.  V3D_GEMM_RTMA: unset / "auto" =
+  // the short-K linear projections (K <= 640: +30 % at K = 320, +10 % at K = 640 on hardware; longer K loses a pipeline
+  // stage to the residual ring and gets slower), "1" = every eligible launch, "0" = never.
   bool rtma = false;
   {
-    static int want_rtma = -1;
-    if (want_rtma < 0) {
+    static int want_rtma = -2;
+    if (want_rtma == -2) {
       const char* v = getenv("V3D_GEMM_RTMA");
-      want_rtma = (v && atoi(v) != 0) ? 1 : 0;
+      want_rtma = (v == nullptr || v[0] == 'a') ? -1 : (atoi(v) != 0 ? 1 : 0);
     }
-    rtma = want_rtma == 1 && epi_kind == EPI_BF16 && e.R1 != nullptr && !pair && bn % 32 == 0 && bn >= 64 &&
-           (reinterpret_cast<uintptr_t>(e.R1) & 15u) == 0;
+    const bool eligible = epi_kind == EPI_BF16 && e.R1 != nullptr && !pair && bn % 32 == 0 && bn >= 64 &&
+                          (reinterpret_cast<uintptr_t>(e.R1) & 15u) == 0;
+    rtma = eligible && (want_rtma == 1 || (want_rtma == -1 && !conv && ntaps == 1 && a->K <= 640 && e.num_m_tiles >= 64));
   }
   if (rtma) epi_kind = EPI_BF16RT;
   CUtensorMap mr;

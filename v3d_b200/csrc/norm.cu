@@ -153,6 +153,185 @@ gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const double* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// GroupNorm in ONE launch: statistics, a grid-wide barrier, then the normalisation of the same rows.
+//   phase 1  every thread sums (x, x^2) of its 8-channel column over its rows; the CTA folds its threads' partials per
+//            group through shared memory + a warp-shuffle tree and writes ONE fp32 (sum, sumsq) pair per group;
+//   barrier  sense-reversing counter in the workspace; the grid is sized to be co-resident (occupancy x SMs);
+//   phase 2  every CTA adds the partials of its sample in fp64, chunk order fixed by the launch geometry (warp-shuffle
+//            tree again) -> mean / rstd, then re-reads its rows in REVERSE order (the rows read last are the ones most
+//            likely still in the 126 MB L2) and writes act((x - mean) rstd gamma + beta).
+// No atomics on data: the result is bit-reproducible run to run.  One launch and one HBM read less than the
+// stats + apply pair, which stays for the frame-sharded path (statistics all-reduce between the two).
+// ------------------------------------------------------------------------------------------------
+struct GnBarrier {
+  unsigned int count;
+  unsigned int gen;
+};
+constexpr int kGnMaxCtas = 4096;                                   // partial slots in the workspace
+constexpr size_t kGnWsBytes = 256 + sizeof(float) * 2 * 32 * kGnMaxCtas;
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(512)
+gn_fused_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, GnBarrier* __restrict__ bar, float2* __restrict__ partial,
+                long long rows_per_sample, int C, long long ldx, int groups, float eps, int silu, int rows_per_cta) {
+  extern __shared__ float s_red[];  // [2][lanes_r][C] thread partials, reused as [groups][2] mean / rstd
+  const int vpr = C >> 3;
+  const int sample = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int lanes_r = blockDim.x / vpr;
+  const int vc = threadIdx.x % vpr;
+  const int rl = threadIdx.x / vpr;
+  const int cg = C / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long row1 = row0 + rows_per_cta;
+  if (row1 > rows_per_sample) row1 = rows_per_sample;
+  const long long srow = static_cast<long long>(sample) * rows_per_sample;
+  const bf16* xb = x + srow * ldx + vc * 8;
+
+  // ---- phase 1: thread partials
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  auto accum = [&](const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+      s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+    }
+  };
+  long long r = row0 + rl;
+  for (; r + static_cast<long long>(kGnUnroll - 1) * lanes_r < row1; r += static_cast<long long>(kGnUnroll) * lanes_r) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k)
+      u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (r + static_cast<long long>(k) * lanes_r) * ldx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) accum(u[k]);
+  }
+  for (; r < row1; r += lanes_r) accum(__ldg(reinterpret_cast<const uint4*>(xb + r * ldx)));
+  {
+    float* ss = s_red + (static_cast<size_t>(rl) * C + vc * 8);
+    float* qq = ss + static_cast<size_t>(lanes_r) * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss[j] = s[j];
+      qq[j] = q[j];
+    }
+  }
+  __syncthreads();
+  // CTA partial of group g = sum over its cg channels x lanes_r row lanes: one warp per group, shuffle tree
+  const int cta_id = sample * chunks + blockIdx.x;
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    const int n = cg * lanes_r;
+    for (int i = lane; i < n; i += 32) {
+      const int rr = i / cg, cc = g * cg + (i - rr * cg);
+      a += s_red[static_cast<size_t>(rr) * C + cc];
+      b += s_red[static_cast<size_t>(lanes_r + rr) * C + cc];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) partial[static_cast<size_t>(cta_id) * groups + g] = make_float2(a, b);
+  }
+  // ---- grid-wide barrier (sense reversal: works for any grid size launch after launch on one stream)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int my_gen = ld_acquire_u32(&bar->gen);
+    __threadfence();
+    const unsigned int prev = atomicAdd(&bar->count, 1u);
+    if (prev == total - 1) {
+      bar->count = 0;
+      __threadfence();
+      st_release_u32(&bar->gen, my_gen + 1);
+    } else {
+      while (ld_acquire_u32(&bar->gen) == my_gen) __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: mean / rstd of this sample's groups (fp64, fixed chunk order), then normalise
+  float* s_stat = s_red;  // [groups][2]
+  const double cnt = static_cast<double>(rows_per_sample) * cg;
+  for (int g = warp; g < groups; g += nwarps) {
+    double a = 0.0, b = 0.0;
+    for (int k = lane; k < chunks; k += 32) {
+      const float2 p = __ldcg(&partial[static_cast<size_t>(sample * chunks + k) * groups + g]);
+      a += static_cast<double>(p.x);
+      b += static_cast<double>(p.y);
+    }
+    a = warp_sum_f64(a);
+    b = warp_sum_f64(b);
+    if (lane == 0) {
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_stat[2 * g] = static_cast<float>(mean);
+      s_stat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vc * 8 + j;
+    const int g = c / cg;
+    const float a = s_stat[2 * g + 1] * __ldg(gamma + c);
+    sc[j] = a;
+    sh[j] = __ldg(beta + c) - s_stat[2 * g] * a;
+  }
+  bf16* yb = y + srow * static_cast<long long>(C) + vc * 8;
+  auto emit = [&](const uint4& u, long long rr) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      float a = fmaf(f.x, sc[2 * j], sh[2 * j]);
+      float b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+      if (silu) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    *reinterpret_cast<uint4*>(yb + rr * static_cast<long long>(C)) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  // reverse order: this thread's rows are row0 + rl + i * lanes_r, i = 0 .. n_i - 1
+  const long long span = row1 - row0 - rl;
+  long long n_i = span > 0 ? (span + lanes_r - 1) / lanes_r : 0;
+  long long i = n_i;
+  for (; i >= kGnUnroll; i -= kGnUnroll) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k)
+      u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (row0 + rl + (i - 1 - k) * lanes_r) * ldx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) emit(u[k], row0 + rl + (i - 1 - k) * lanes_r);
+  }
+  for (; i > 0; --i) {
+    const long long rr = row0 + rl + (i - 1) * lanes_r;
+    emit(__ldg(reinterpret_cast<const uint4*>(xb + rr * ldx)), rr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over C (<= 2048), one warp per row, row held in registers.
 //   z = x[row] + add[row / rows_per_frame]   (add optional, fp32)
 //   ysum[row] = bf16(z)                      (optional)
@@ -520,6 +699,60 @@ int v3d_groupnorm_apply(const void* x, void* y, const void* stats, const void* g
   return V3D_OK;
 }
 
+/* Bytes of the workspace v3d_groupnorm needs (barrier words + per-CTA partials); the caller allocates it once per
+ * stream, ZEROED, and passes the same buffer to every call on that stream. */
+int64_t v3d_groupnorm_workspace_bytes(void) { return static_cast<int64_t>(kGnWsBytes); }
+
+/* y[dense, ld=C] = act(GroupNorm(x; gamma, beta, eps)) in ONE launch (statistics + grid barrier + apply); same
+ * operand meaning as the v3d_groupnorm_stats / v3d_groupnorm_apply pair it replaces on the unsharded path
+ * (GroupNorm32 + SiLU openaimodel.py:267-271,300-303, diffusionmodules/util.py:259-276; Normalize model.py:52-55,
+ * attention.py:130-133).  Deterministic (no atomics on data).  Calls sharing a workspace must be stream-ordered. */
+int v3d_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows_per_sample,
+                  int32_t nsamples, int32_t C, int32_t ldx, int32_t groups, float eps, int32_t silu,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!x || !y || !gamma || !beta || !workspace || C % 8 != 0 || groups <= 0 || groups > 32 || C % groups != 0 ||
+      C / 8 > 512 || ldx % 8 != 0 || rows_per_sample <= 0 || nsamples <= 0 ||
+      workspace_bytes < static_cast<int64_t>(kGnWsBytes)) {
+    set_error("v3d_groupnorm: bad args C=%d groups=%d ldx=%d workspace=%lld", C, groups, ldx,
+              static_cast<long long>(workspace_bytes));
+    return V3D_ERR_BAD_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vpr = C / 8;
+  const int lanes_r = kGnThreads / vpr > 0 ? kGnThreads / vpr : 1;
+  const int threads = vpr * lanes_r;
+  const size_t smem = sizeof(float) * 2 * static_cast<size_t>(lanes_r) * C;
+  // co-resident capacity of this launch shape (the barrier needs every CTA on the device at once)
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
+  if (e != cudaSuccess || per_sm < 1) {
+    set_error("v3d_groupnorm: occupancy query failed (%s)", cudaGetErrorString(e));
+    return V3D_ERR_CUDA;
+  }
+  if (per_sm > 4) per_sm = 4;
+  long long cap = static_cast<long long>(per_sm) * num_sms();
+  if (cap > kGnMaxCtas) cap = kGnMaxCtas;
+  if (nsamples > cap) {
+    // more samples than co-resident CTAs: fall back to the two-kernel form on the caller's side
+    set_error("v3d_groupnorm: %d samples exceed the co-resident grid (%lld CTAs)", nsamples, cap);
+    return V3D_ERR_UNSUPPORTED;
+  }
+  long long chunks = cap / nsamples;
+  long long max_chunks = (rows_per_sample + 4LL * lanes_r - 1) / (4LL * lanes_r);  // >= 4 rows per thread
+  if (max_chunks < 1) max_chunks = 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  long long rpc = (rows_per_sample + chunks - 1) / chunks;
+  chunks = (rows_per_sample + rpc - 1) / rpc;
+  dim3 grid(static_cast<unsigned>(chunks), nsamples);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  gn_fused_kernel<<<grid, threads, smem, st>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), static_cast<const float*>(gamma),
+      static_cast<const float*>(beta), reinterpret_cast<GnBarrier*>(ws), reinterpret_cast<float2*>(ws + 256),
+      rows_per_sample, C, ldx, groups, eps, silu, static_cast<int>(rpc));
+  V3D_CHECK_LAUNCH("gn_fused_kernel");
+  return V3D_OK;
+}
+
 /* LayerNorm (attention.py:525-527, video_attention.py:51,79,93-94) with the optional fused
  * "x_mix = x + emb" of video_attention.py:286-287 (add = per-frame fp32 vectors, ysum receives x+emb). */
 int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const void* gamma, const void* beta,
@@ -537,7 +770,14 @@ int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const voi
     const int lpr = C / 40;
     const long long rows_per_cta = 8LL * (32 / lpr);
     long long nb = (rows + rows_per_cta - 1) / rows_per_cta;
-    const long long cap2 = 16LL * num_sms();
+    // grid-stride over rows: V3D_LN_CTAS_PER_SM (tuning knob) bounds the grid in CTAs per SM
+    static int ln_ctas = 0;
+    if (ln_ctas == 0) {
+      const char* v = getenv("V3D_LN_CTAS_PER_SM");
+      ln_ctas = v ? atoi(v) : 16;
+      if (ln_ctas < 1) ln_ctas = 1;
+    }
+    const long long cap2 = static_cast<long long>(ln_ctas) * num_sms();
     if (nb > cap2) nb = cap2;
 #define V3D_LN40(L)                                                                                              \
   layernorm40_kernel<L><<<static_cast<unsigned>(nb), 256, 0, st>>>(                                             \

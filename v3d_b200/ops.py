@@ -116,6 +116,25 @@ def groupnorm_apply(x: torch.Tensor, y: torch.Tensor, stats: torch.Tensor, gamma
     return y
 
 
+def groupnorm_workspace(device) -> torch.Tensor:
+    """Zeroed workspace of the single-launch GroupNorm (barrier state + per-CTA partials); one per stream."""
+    return torch.zeros(int(_lib.load().v3d_groupnorm_workspace_bytes()), device=device, dtype=torch.uint8)
+
+
+def groupnorm(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, rows_per_sample: int,
+              nsamples: int, c: int, eps: float, silu: bool, workspace: torch.Tensor, ldx: Optional[int] = None,
+              groups: int = 32) -> torch.Tensor:
+    """y = act(GroupNorm(x)) in one launch (statistics, grid barrier, apply); deterministic."""
+    _need(x, torch.bfloat16, "groupnorm x")
+    _need(gamma, torch.float32, "groupnorm gamma")
+    _need(workspace, torch.uint8, "groupnorm workspace")
+    _lib.check(_lib.load().v3d_groupnorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                         rows_per_sample, nsamples, c, c if ldx is None else ldx, groups, eps,
+                                         1 if silu else 0, workspace.data_ptr(), workspace.numel(), _stream()),
+               "v3d_groupnorm")
+    return y
+
+
 def layernorm(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, rows: int, c: int,
               eps: float = 1e-5, add: Optional[torch.Tensor] = None, ysum: Optional[torch.Tensor] = None,
               rows_per_frame: int = 1) -> torch.Tensor:

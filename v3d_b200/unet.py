@@ -169,10 +169,22 @@ class KernelModule(nn.Module):
             return stats, True
         return torch.empty(nsamples, 32, 2, device=dev, dtype=torch.float64), False
 
+    def _gn_workspace(self, dev) -> torch.Tensor:
+        """Barrier state + partials of the single-launch GroupNorm: one zeroed buffer per module and device (every
+        launch of this module is issued on one stream; captured CUDA graphs hold its address)."""
+        ws = getattr(self, "_gn_ws", None)
+        if ws is None or ws.device != dev:
+            ws = ops.groupnorm_workspace(dev)
+            object.__setattr__(self, "_gn_ws", ws)
+        return ws
+
     def _gn(self, P: dict, key: str, x: torch.Tensor, rows_per_sample: int, nsamples: int, c: int, eps: float,
             silu: bool) -> torch.Tensor:
-        stats, pre_zeroed = self._take_stats(nsamples, x.device)
         y = torch.empty(x.shape[0], c, device=x.device, dtype=torch.bfloat16)
+        if nsamples <= 256 and os.environ.get("V3D_GN_FUSED", "1") != "0":
+            return ops.groupnorm(x, y, P[key + ".weight"], P[key + ".bias"], rows_per_sample, nsamples, c, eps, silu,
+                                 self._gn_workspace(x.device))
+        stats, pre_zeroed = self._take_stats(nsamples, x.device)
         ops.groupnorm_stats(x, stats, rows_per_sample, nsamples, c, pre_zeroed=pre_zeroed)
         ops.groupnorm_apply(x, y, stats, P[key + ".weight"], P[key + ".bias"], rows_per_sample, nsamples, c, eps,
                             silu)
