@@ -218,6 +218,42 @@ int v3d_decode_to_u8(const void* x, int64_t ldx, int32_t src_fp32, void* y, int6
 /* same, from NCHW fp32 frames [T][3][HW] (decode_first_stage's return layout) to uint8 [T][HW][3]. */
 int v3d_frames_nchw_to_u8(const void* x, void* y, int32_t T, int64_t HW, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One-sided exchanges over NVLink peer memory (peer.cu): the transport of the frame-sharded path - ONE image over
+ * several GPUs of a box (BASELINE.json north_star).  They replace, on the data path, the three
+ * torch.distributed exchanges that the reference's single-GPU modules imply once the T frames are split over ranks:
+ * the temporal-attention K|V all-gather (video_attention.py:114-125 around attention.py:337-341), the 1-frame halos
+ * of the (3,1,1) temporal convolutions (video_model.py:42-55, temporal_ae.py:94-99) and the (sum, sumsq) all-reduce
+ * of the 3-D GroupNorm (openaimodel.py:267-271 with dims=3).  Every rank owns an arena (v3d_peer_alloc) that the
+ * other ranks map through a 64-byte IPC handle; kernels then store straight into the mapped arenas and raise /
+ * wait on epoch-valued flag words, so a whole sharded forward is stream-ordered and CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------ */
+#define V3D_PEER_MAX_SEG 16
+#define V3D_PEER_MAX_FLAG 16
+#define V3D_PEER_MAX_RANKS 8
+/* zeroed device memory that can be exported (plain cudaMalloc, not the framework's caching allocator) */
+int v3d_peer_alloc(int64_t bytes, void** out);
+int v3d_peer_free(void* p);
+/* 64-byte handle of an arena (cudaIpcGetMemHandle) / mapping of another rank's arena (cudaIpcOpenMemHandle) */
+int v3d_peer_export(const void* p, void* handle64);
+int v3d_peer_import(const void* handle64, void** out);
+int v3d_peer_close(void* p);
+/* *epoch += 1 on the stream: once at the start of every sharded forward (flags carry the epoch) */
+int v3d_peer_epoch_bump(void* epoch, void* stream);
+/* copy nseg contiguous segments src[i] -> dst[i] (bytes[i], multiples of 16; dst may be mapped peer memory), then -
+ * once all stores are fenced system-wide - store *epoch into the nflag flag words (usually in the receivers' arenas).
+ * done_counter: one zeroed u32 of local scratch per stream. */
+int v3d_peer_put(int32_t nseg, const void* const* src, void* const* dst, const int64_t* bytes, int32_t nflag,
+                 void* const* flags, const void* epoch, void* done_counter, void* stream);
+/* block the stream until every flag word >= *epoch (bounded: after ~20 s the site id is recorded in *status) */
+int v3d_peer_wait(int32_t nflag, const void* const* flags, const void* epoch, void* status, int32_t site,
+                  void* stream);
+/* stats[n] (fp64) := scale * sum over ranks, rank-ordered (bit-identical on every rank): slot_base[r] / flag_base[r]
+ * = rank r's slot area [world][n] doubles / flag area [world] words of this exchange site. */
+int v3d_peer_allreduce_f64(void* stats, int32_t n, double scale, int32_t world, int32_t rank,
+                           void* const* slot_base, void* const* flag_base, const void* epoch, void* status,
+                           int32_t site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -379,7 +379,7 @@ def test_schedule_cost_accounting_matches_known_flop_budget():
     tf = lambda book: sum(v[1] for v in book.values()) / 1e12          # noqa: E731
     assert 43.0 < tf(full["unet_forward"]) < 45.68                       # 45.68 TF reference accounting, minus 1.94 TF
     assert abs(tf(full["decode"]) - 54.77) < 0.5                         # decoder: nothing is skipped
-    assert full["unet_forward"]["gemm.conv3x3"][0] == 48 and full["unet_forward"]["groupnorm_apply"][0] == 105
+    assert full["unet_forward"]["gemm.conv3x3"][0] == 48 and full["unet_forward"]["groupnorm"][0] == 105  # one launch per norm
     cfg = sc.run(18, 64, "cfg", 2, 0, 25)
     assert abs(tf(cfg["unet_forward"]) / tf(full["unet_forward"]) - 0.5) < 0.01
     assert cfg["comm_per_unet_forward"]["cfg_gather"] == [1, 18 * 4 * 64 * 64 * 4]

@@ -119,8 +119,9 @@ def test_single_rank_view_shard_equals_unsharded_engine():
 # --------------------------------------------------------------------------------------------------------------
 # model level
 # --------------------------------------------------------------------------------------------------------------
-def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, T: int, q):
+def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, T: int, transport: str, q):
     sys.path.insert(0, ROOT)
+    os.environ["V3D_SHARD_TRANSPORT"] = transport
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -146,7 +147,7 @@ def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool
     to = lambda d: {k: v.to(dev) for k, v in d.items()}
     c, uc = to(c), to(uc)
     vs = ViewShard.create(T)
-    res = {"rank": rank, "block": (vs.t0, vs.tl)}
+    res = {"rank": rank, "block": (vs.t0, vs.tl), "peer": vs.peer is not None}
 
     # one UNet forward, sharded vs unsharded
     xin = torch.cat([torch.cat([x.to(dev)] * 2), torch.cat([uc["concat"], c["concat"]])], 1)   # [2T, 8, hw, hw]
@@ -177,14 +178,19 @@ def _engine_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool
     dist.destroy_process_group()
 
 
-def _run_engine_pair(backend: str, one_gpu: bool, T: int = 5, world: int = 2):
+def _run_engine_pair(backend: str, one_gpu: bool, T: int = 5, world: int = 2, transport: str = "auto"):
+    """transport: "auto" = one-sided peer memory over NCCL groups, torch.distributed collectives over gloo;
+    "peer" / "nccl" force one (peer works between two processes on ONE GPU too: IPC-mapped memory of the same device)"""
     sys.path.insert(0, str(Path(ROOT) / "tests"))
     from mp_util import run_workers
 
-    res = sorted(run_workers(_engine_worker, world, (backend, one_gpu, T), timeout=900), key=lambda r: r["rank"])
-    print(backend, res)
+    res = sorted(run_workers(_engine_worker, world, (backend, one_gpu, T, transport), timeout=900),
+                 key=lambda r: r["rank"])
+    print(backend, transport, res)
     assert [r["block"] for r in res] == [(0, 3), (3, 2)]
+    want_peer = transport == "peer" or (transport == "auto" and backend == "nccl")
     for r in res:
+        assert r["peer"] == want_peer, r
         assert r["finite"]
         assert r["unet_rel"] <= 3e-2, r
         assert r["frames_rel"] <= 3e-2 and r["gathered_rel"] <= 3e-2, r
@@ -196,16 +202,29 @@ def test_view_sharded_engine_matches_unsharded_one_gpu_gloo():
     _run_engine_pair("gloo", one_gpu=True)
 
 
+def test_view_sharded_engine_peer_transport_one_gpu():
+    """The one-sided peer-memory transport (csrc/peer.cu: IPC-mapped arenas, epoch flags, the sharded forward captured
+    into a CUDA graph) between two processes that share cuda:0 - the arenas are mapped through the same IPC handles as
+    across NVLink, so the whole protocol (sites, rotation, flags, statistics all-reduce) runs on a one-GPU box."""
+    _run_engine_pair("gloo", one_gpu=True, transport="peer")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_view_sharded_engine_matches_unsharded_nccl():
-    _run_engine_pair("nccl", one_gpu=False)
+    _run_engine_pair("nccl", one_gpu=False)                       # default transport over NCCL groups: peer memory
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_view_sharded_engine_matches_unsharded_nccl_collectives():
+    _run_engine_pair("nccl", one_gpu=False, transport="nccl")    # torch.distributed collectives on the data path
 
 
 # --------------------------------------------------------------------------------------------------------------
 # CFG-pair split and composite plans (ShardPlan)
 # --------------------------------------------------------------------------------------------------------------
-def _plan_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, T: int, mode: str, q):
+def _plan_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, T: int, mode: str, transport: str, q):
     sys.path.insert(0, ROOT)
+    os.environ["V3D_SHARD_TRANSPORT"] = transport
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -240,14 +259,17 @@ def _plan_worker(rank: int, world: int, port: int, backend: str, one_gpu: bool, 
     dist.destroy_process_group()
 
 
-def _run_plan(mode: str, world: int, backend: str, one_gpu: bool, T: int = 5):
+def _run_plan(mode: str, world: int, backend: str, one_gpu: bool, T: int = 5, transport: str = "auto"):
     sys.path.insert(0, str(Path(ROOT) / "tests"))
     from mp_util import run_workers
 
-    res = sorted(run_workers(_plan_worker, world, (backend, one_gpu, T, mode), timeout=900), key=lambda r: r["rank"])
-    print(mode, backend, res)
+    res = sorted(run_workers(_plan_worker, world, (backend, one_gpu, T, mode, transport), timeout=900),
+                 key=lambda r: r["rank"])
+    print(mode, backend, transport, res)
     covered = []
+    want_peer = transport == "peer" or (transport == "auto" and backend == "nccl")
     for r in res:
+        assert r["plan"]["transport"].startswith("peer") == want_peer, r
         covered += list(range(r["decode_block"][0], sum(r["decode_block"])))
         assert r["finite"] and r["local_rel"] <= 3e-2 and r["gathered_rel"] <= 3e-2, r
         assert r["plan"]["exchanges"]["cfg_gather"] == 2
@@ -260,6 +282,14 @@ def test_cfg_split_engine_matches_unsharded_one_gpu_gloo():
 
 def test_cfg_views_engine_matches_unsharded_one_gpu_gloo():
     _run_plan("cfg+views", 4, "gloo", one_gpu=True)
+
+
+def test_cfg_split_engine_peer_transport_one_gpu():
+    _run_plan("cfg", 2, "gloo", one_gpu=True, transport="peer")
+
+
+def test_cfg_views_engine_peer_transport_one_gpu():
+    _run_plan("cfg+views", 4, "gloo", one_gpu=True, transport="peer")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")

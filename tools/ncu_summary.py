@@ -116,7 +116,42 @@ def source(path: str, top: int = 25) -> None:
         print(f"| {s} | {100 * s / max(total, 1):.1f}% | {ex} | `{src}` |")
 
 
+def traffic(path: str) -> None:
+    """`roofline.traffic` of bench.py: DRAM bytes (read + write) per launch of every captured kernel of a `--set full`
+    raw page, stamped with the digest of the kernel sources the capture was taken from (bench.py drops the object when
+    the sources have changed since).  python tools/ncu_summary.py traffic /tmp/raw.csv > profiles/traffic_r2.json"""
+    import json
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+
+    rows = _rows(path)
+    head, units = rows[0], rows[1]
+    ik = head.index("Kernel Name")
+    col = {h: i for i, h in enumerate(head)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(r, name):
+        i = col[name]
+        return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+
+    out = {"csrc_digest": bench.csrc_digest(), "source": "ncu --set full --clock-control none (tools/microbench.py "
+           "ncu_set: every kernel family at its V3D_512 top-level shape, second launch of each)", "kernels": {}}
+    seen = {}
+    for r in rows[2:]:
+        if len(r) <= ik:
+            continue
+        k = short_kernel(r[ik])
+        seen[k] = seen.get(k, 0) + 1
+        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+        dur = float(r[col["gpu__time_duration.sum"]].replace(",", ""))
+        out["kernels"][f"{k} #{seen[k]}"] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "traffic": rd + wr,
+                                            "duration_" + units[col["gpu__time_duration.sum"]]: dur}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "raw", "source"):
+    if len(sys.argv) < 3 or sys.argv[1] not in ("launches", "raw", "source", "traffic"):
         raise SystemExit(__doc__)
-    {"launches": launches, "raw": raw, "source": source}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "source": source, "traffic": traffic}[sys.argv[1]](sys.argv[2])

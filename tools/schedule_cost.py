@@ -178,7 +178,7 @@ class DryShard(ViewShard):
         self._comm("halo", nb * neighbours * frame)
         return pad
 
-    def gather_rows(self, send):
+    def gather_rows(self, send, buf=None, filled_rows=None):
         self._comm("kv_allgather", send.numel() * send.element_size() * (self.world > 1))
         return send.new_empty((self.world * send.shape[0],) + tuple(send.shape[1:]))
 

@@ -56,6 +56,16 @@ SIGNATURES = {
     "v3d_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
     "v3d_softmax_rows": (C.c_int, [_vp, _i64, _i32, _f32, _vp]),
     "v3d_softmax_rows_f32": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),
+    # peer.cu
+    "v3d_peer_alloc": (C.c_int, [_i64, C.POINTER(_vp)]),
+    "v3d_peer_free": (C.c_int, [_vp]),
+    "v3d_peer_export": (C.c_int, [_vp, _vp]),
+    "v3d_peer_import": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "v3d_peer_close": (C.c_int, [_vp]),
+    "v3d_peer_epoch_bump": (C.c_int, [_vp, _vp]),
+    "v3d_peer_put": (C.c_int, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, C.POINTER(_vp), _vp, _vp, _vp]),
+    "v3d_peer_wait": (C.c_int, [_i32, C.POINTER(_vp), _vp, _vp, _i32, _vp]),
+    "v3d_peer_allreduce_f64": (C.c_int, [_vp, _i32, C.c_double, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i32, _vp]),
     # attention.cu
     "v3d_attention_spatial": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "v3d_attention_spatial_mma": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),

@@ -196,7 +196,9 @@ gn_fused_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* _
   const int vc = threadIdx.x % vpr;
   const int rl = threadIdx.x / vpr;
   const int cg = C / groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+  // only FULL warps take part in the shuffle trees (240-thread CTAs end in a 16-lane warp: a full-mask shuffle there
+  // would read lanes that do not exist); a trailing partial warp gets warp id >= nwarps and skips those loops
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   long long row1 = row0 + rows_per_cta;
   if (row1 > rows_per_sample) row1 = rows_per_sample;
@@ -238,7 +240,7 @@ gn_fused_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* _
   __syncthreads();
   // CTA partial of group g = sum over its cg channels x lanes_r row lanes: one warp per group, shuffle tree
   const int cta_id = sample * chunks + blockIdx.x;
-  for (int g = warp; g < groups; g += nwarps) {
+  for (int g = warp < nwarps ? warp : groups; g < groups; g += nwarps) {
     float a = 0.f, b = 0.f;
     const int n = cg * lanes_r;
     for (int i = lane; i < n; i += 32) {
@@ -269,7 +271,7 @@ gn_fused_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* _
   // ---- phase 2: mean / rstd of this sample's groups (fp64, fixed chunk order), then normalise
   float* s_stat = s_red;  // [groups][2]
   const double cnt = static_cast<double>(rows_per_sample) * cg;
-  for (int g = warp; g < groups; g += nwarps) {
+  for (int g = warp < nwarps ? warp : groups; g < groups; g += nwarps) {
     double a = 0.0, b = 0.0;
     for (int k = lane; k < chunks; k += 32) {
       const float2 p = __ldcg(&partial[static_cast<size_t>(sample * chunks + k) * groups + g]);

@@ -284,6 +284,8 @@ class VideoDecoder(KernelModule):
     def _run(self, P: dict, z: torch.Tensor, B: int, T: int, nb: int, H: int, W: int) -> torch.Tensor:
         """The launch schedule of one decode (Decoder.forward, model.py:715-748, through VideoDecoder)."""
         vs = self.view_shard
+        if vs is not None:
+            vs.begin("decoder")
         dev, zc = z.device, self.z_channels
         n_norms = 4 * sum(1 for n, _, _ in self._blocks() if not n.startswith("@")) + 2
         object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
@@ -316,7 +318,7 @@ class VideoDecoder(KernelModule):
             # AE3DConv's time_mix_conv (temporal_ae.py:101-107) is one more (3,1,1) conv: conv_out lands in the
             # interior of a halo'd fp32 buffer, the mix runs over T + 2 frames and the two halo frames are dropped
             cop = P["conv_out.weight"].shape[0]
-            pad = torch.empty(1, T + 2, h * w, cop, device=dev, dtype=torch.float32)
+            pad = vs.new_pad((1, T + 2, h * w, cop), torch.float32, dev)
             self._conv3x3(P, "conv_out", a, B, h, w, ch, out=pad[0, 1:T + 1].view(B * h * w, cop))
             vs.exchange_halos(pad)
             full = torch.empty(T + 2, self.out_ch, h, w, device=dev, dtype=torch.float32)

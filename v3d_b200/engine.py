@@ -9,6 +9,7 @@ from __future__ import annotations
 import contextlib
 import copy
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -204,7 +205,10 @@ class DiffusionEngine(nn.Module):
             off = dvs.t0 - (vs.t0 if vs is not None else 0)
             assert 0 <= off and off + dvs.tl <= z.shape[0], "decode blocks must lie inside the sampling blocks"
             decoder.view_shard = dvs
-            return self.first_stage_model.decode(1.0 / self.scale_factor * z[off:off + dvs.tl].contiguous(),
-                                                 timesteps=dvs.tl)
+            out = self.first_stage_model.decode(1.0 / self.scale_factor * z[off:off + dvs.tl].contiguous(),
+                                                timesteps=dvs.tl)
+            if os.environ.get("V3D_PEER_CHECK", "1") != "0":
+                plan.check_status()      # a one-sided exchange that timed out invalidates the image: fail loudly
+            return out
         finally:
             unet.view_shard = decoder.view_shard = None

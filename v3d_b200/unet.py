@@ -199,7 +199,7 @@ class KernelModule(nn.Module):
         stats, pre_zeroed = self._take_stats(nb, x.device)
         ops.groupnorm_stats(x, stats, tl * hw, nb, c, pre_zeroed=pre_zeroed)
         vs.allreduce_stats_(stats)
-        pad = torch.empty(nb, tl + 2, hw, c, device=x.device, dtype=torch.bfloat16)
+        pad = vs.new_pad((nb, tl + 2, hw, c), torch.bfloat16, x.device)
         for b in range(nb):
             ops.groupnorm_apply(x[b * tl * hw:(b + 1) * tl * hw], pad[b, 1:tl + 1], stats[b:b + 1],
                                 P[key + ".weight"], P[key + ".bias"], tl * hw, 1, c, eps, silu)
@@ -696,8 +696,10 @@ class VideoUNet(KernelModule):
             assert time_context is not None and time_context.shape[0] == nb and time_context.ndim == 3, \
                 "view-sharded forward needs time_context = context of frame 0 of each video, [nb, 1, ctx]"
             ctx2d = torch.cat([ctx2d, time_context.float().reshape(nb, -1).to(dev)], dim=0)
-            # collectives inside a captured graph are opt-in until validated on hardware
-            graphs = graphs and os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1" and not vs._via_host(x)
+            # the one-sided peer transport is stream-ordered kernels only: always capturable.  torch.distributed
+            # collectives inside a captured graph stay opt-in (V3D_VIEWSHARD_GRAPH=1)
+            graphs = graphs and (vs.peer is not None or
+                                 (os.environ.get("V3D_VIEWSHARD_GRAPH", "0") == "1" and not vs._via_host(x)))
         args = (x.float().contiguous(), timesteps.float().contiguous(), ctx2d.contiguous(), y.float().contiguous())
         return args, (B, T, nb, H, W), graphs
 
@@ -842,10 +844,11 @@ class VideoUNet(KernelModule):
         else:
             # frame-sharded: all-gather the packed K|V rows of every rank's frames, attend in place through the
             # per-frame row table; the time context (global frame 0 of each CFG half) is rows B.. of `cross`
-            send = torch.empty(nb * vs.tmax * hw, 2 * c, device=dev, dtype=torch.bfloat16)
+            kv_buf, send = vs.kv_slots(nb, hw, 2 * c, torch.bfloat16, dev)
             ops.copy_channels(qkv[:, c:], 3 * c, send, 2 * c, rows, 2 * c)
             kv_row, kv_bstride = vs.kv_table(nb, hw)
-            ops.attention_temporal_kv(qkv, vs.gather_rows(send), o, nb, T, hw, heads, kv_row, kv_bstride, scale)
+            ops.attention_temporal_kv(qkv, vs.gather_rows(send, kv_buf, rows), o, nb, T, hw, heads, kv_row,
+                                      kv_bstride, scale)
             tc_bias, tc_ld = cross[B:, ot:], X
         self._linear(P, ts + ".attn1.to_out.0", o, rows, out=xm, r1=xm, s1=1.0,
                      fbias=tc_bias, ldfb=tc_ld, rows_per_frame=T * hw)
@@ -857,6 +860,8 @@ class VideoUNet(KernelModule):
         return self._linear(P, nm + ".proj_out", t, rows, out=xn, r1=x, s1=1.0)
 
     def _run(self, P, x, timesteps, ctx2d, y, B, T, nb, H, W, dev):
+        if self.view_shard is not None:
+            self.view_shard.begin("unet")     # one-sided transport: rewind the exchange sites, bump the epoch
         n_norms = sum({"res": 4, "attn": 1, "out": 1}.get(st.kind, 0) for st in self.steps)
         object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
         try:
