@@ -132,7 +132,7 @@ def groupnorm_workspace(device):
 
 def groupnorm(x, y, gamma, beta, rows_per_sample, nsamples, c, eps, silu, workspace, ldx=None, groups=32):
     """single-launch GroupNorm = statistics + apply (one tick: one launch)"""
-    st = torch.zeros(nsamples, groups, 2, dtype=torch.float64)
+    st = torch.zeros(nsamples, groups, 2, dtype=torch.float64, device=x.device)
     groupnorm_stats(x, st, rows_per_sample, nsamples, c, ldx=ldx, groups=groups, pre_zeroed=True)
     groupnorm_apply(x, y, st, gamma, beta, rows_per_sample, nsamples, c, eps, silu, ldx=ldx, groups=groups)
     _tick(-1)

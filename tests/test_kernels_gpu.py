@@ -322,7 +322,7 @@ def test_softmax_rows():
 # attention
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nb,ntok,heads", [(2, 16, 4), (3, 64, 20), (2, 256, 10), (2, 1024, 5), (1, 4096, 5),
-                                           (2, 200, 2), (1, 1000, 3)])
+                                           (2, 200, 2), (1, 1000, 3), (2, 300, 2), (1, 600, 1), (3, 2048, 2)])
 @pytest.mark.parametrize("impl", ["tcgen05", "mma"])
 def test_attention_spatial(nb, ntok, heads, impl):
     c = heads * 64

@@ -59,7 +59,8 @@ for stage in "$@"; do
       V3D_RUN_UNVALIDATED=1 run 600 attn_poly_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "attention_poly_exp2"
       for k in 0 1 2 3; do V3D_ATTN_POLY=$k run 300 "micro_attn_poly$k.log" $PY tools/microbench.py attn; done ;;
     bench)
-      run 900 bench.json $PY bench.py --steps 3 --warmup 3
+      run 900 bench.json $PY bench.py --steps 3 --warmup 3 ;;
+    bench_ref)   # host cores only (charged GPU time all the same): run it sparingly
       run 900 bench_ref.json $PY bench.py --impl reference --steps 2 --warmup 1 ;;
     sweep)
       run 1500 sweep.log $PY tools/sweep.py ;;
@@ -67,11 +68,11 @@ for stage in "$@"; do
       V3D_GEMM_2CTA=1 run 900 bench_pair.json $PY bench.py --steps 3 --warmup 3 --no-cpu-baseline ;;
     ncu_launches)
       V3D_CUDA_GRAPH=0 run 1200 ncu_launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
-        --log-file gpurun_out/launches.csv $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline ;;
+        --log-file gpurun_out/launches.csv $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline --no-parity ;;
     ncu_full)
       for k in gemm_tc_kernel attn_tc_kernel gn_stats_kernel gn_apply_kernel layernorm attn_temporal_kernel; do
         V3D_CUDA_GRAPH=0 run 600 "ncu_full_$k.log" ncu --set full --clock-control none --import-source on \
-          -k "regex:$k" -s 40 -c 3 -o "gpurun_out/full_$k" -f $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline
+          -k "regex:$k" -s 40 -c 3 -o "gpurun_out/full_$k" -f $PY bench.py --steps 1 --warmup 0 --edm-steps 1 --no-cpu-baseline --no-parity
       done ;;
     ncu_set)
       # ONE ncu --set full run over every kernel family at its V3D_512 top-level shape (tools/microbench.py ncu_set)

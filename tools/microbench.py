@@ -124,10 +124,14 @@ def bench_norm(out):
         st = torch.empty(ns, 32, 2, device=DEV, dtype=torch.float64)
         ms1 = timeit(lambda: ops.groupnorm_stats(x, st, rows, ns, c), iters=5)
         ms2 = timeit(lambda: ops.groupnorm_apply(x, y, st, g, b, rows, ns, c, 1e-5, True), iters=5)
+        ws = ops.groupnorm_workspace(DEV)
+        ms3 = timeit(lambda: ops.groupnorm(x, y, g, b, rows, ns, c, 1e-5, True, ws), iters=5)
         gb1 = x.numel() * 2 / ms1 / 1e6
         gb2 = x.numel() * 4 / ms2 / 1e6
-        print(f"{name:18s} stats {ms1:7.3f} ms {gb1:7.0f} GB/s ({100 * gb1 / PEAK_GB:4.1f}%)  apply {ms2:7.3f} ms {gb2:7.0f} GB/s ({100 * gb2 / PEAK_GB:4.1f}%)")
-        out.append(dict(kind="gn", name=name, stats_ms=ms1, apply_ms=ms2, stats_gbs=gb1, apply_gbs=gb2))
+        gb3 = x.numel() * 4 / ms3 / 1e6
+        print(f"{name:18s} stats {ms1:7.3f} ms {gb1:7.0f} GB/s ({100 * gb1 / PEAK_GB:4.1f}%)  apply {ms2:7.3f} ms {gb2:7.0f} GB/s ({100 * gb2 / PEAK_GB:4.1f}%)"
+              f"  one-launch {ms3:7.3f} ms {gb3:7.0f} GB/s ({100 * gb3 / PEAK_GB:4.1f}% of peak on read-once + write-once bytes; pair {ms1 + ms2:7.3f} ms)")
+        out.append(dict(kind="gn", name=name, stats_ms=ms1, apply_ms=ms2, fused_ms=ms3, stats_gbs=gb1, apply_gbs=gb2, fused_gbs=gb3))
     for name, rows, c in [("ln L0", 36 * 4096, 320), ("ln L1", 36 * 1024, 640), ("ln L2", 36 * 256, 1280)]:
         x = bf(rows, c)
         y = torch.empty_like(x)
@@ -230,11 +234,14 @@ if __name__ == "__main__":
         bias, bias8 = torch.randn(c, device=DEV), torch.randn(8 * c, device=DEV)
         sc = torch.randn(4 * 4096, 4096, device=DEV)
         pr = torch.empty(4 * 4096, 4096, device=DEV, dtype=torch.bfloat16)
+        gws = ops.groupnorm_workspace(DEV)
         for _ in range(2):
             ops.groupnorm_stats(x, st, rows, ns, c)
             ops.groupnorm_apply(x, y, st, g, b, rows, ns, c, 1e-5, True)
             ops.groupnorm_stats(x, st[:2], 18 * rows, 2, c)
             ops.groupnorm_apply(x, y, st[:2], g, b, 18 * rows, 2, c, 1e-5, True)
+            ops.groupnorm(x, y, g, b, rows, ns, c, 1e-5, True, gws)
+            ops.groupnorm(x, y, g, b, 18 * rows, 2, c, 1e-5, True, gws)
             ops.layernorm(x, y, g, b, ns * rows, c)
             ops.attention_temporal(qkv, o, 2, 18, rows, 5, 0.125)
             ops.attention_spatial(qkv, o, ns, rows, 5, 0.125)

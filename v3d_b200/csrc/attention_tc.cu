@@ -313,6 +313,303 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two query tiles per CTA (256 queries x one (sample, head)), ONE CTA per SM: the same dataflow as attn_tc_kernel with
+//   * two softmax groups of four warps (group g owns query tile g: its S double buffer, its P double buffer and its O
+//     accumulator in TMEM), sharing every K/V tile that TMA brings in (half the K/V traffic per query);
+//   * the scores of tile j+1 pulled from TMEM into a SECOND register set while the exponentials of tile j are computed
+//     (the 1-CTA/SM register budget pays for it), so the tcgen05.ld latency and the wait for the next QK^T sit under
+//     the MUFU stream instead of in front of it;
+//   * a tree row maximum (four independent FMNMX chains instead of one 32-deep chain).
+// The tensor pipe alternates S_0, S_1, P_0 V, P_1 V: while one group is in its exponentials the other group's MMAs run.
+// TMEM: S[g][b] at columns g*128 + b*64 (256), O[g] at 256 + g*64 (128): 384 of a 512-column allocation.
+// ------------------------------------------------------------------------------------------------
+constexpr int A2_BM = 256;
+constexpr int A2_THREADS = 320;
+constexpr int A2_KVSTAGES = 4;
+constexpr int A2_OFF_Q = 0;                                          // 2 x 16 KB
+constexpr int A2_OFF_K = A2_OFF_Q + 2 * AT_QTILE;
+constexpr int A2_OFF_V = A2_OFF_K + A2_KVSTAGES * AT_KTILE;
+constexpr int A2_OFF_P = A2_OFF_V + A2_KVSTAGES * AT_KTILE;          // [g][b]: 4 x 16 KB
+constexpr int A2_OFF_BAR = A2_OFF_P + 4 * AT_QTILE;
+constexpr int A2_SMEM = A2_OFF_BAR + 512;
+constexpr uint32_t A2_TMEM_COLS = 512;
+
+__global__ void __maxnreg__(200)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV, bf16* __restrict__ O, long long ldo, int ntok,
+                float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t at_smem[];
+  uint8_t* smem = at_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;     // [4]
+  uint64_t* kv_empty = bars + 5;    // [4]
+  uint64_t* s_full = bars + 9;      // [g*2 + b]
+  uint64_t* s_empty = bars + 13;    // [g*2 + b]  128 arrivals
+  uint64_t* p_ready = bars + 17;    // [g*2 + b]  128 arrivals
+  uint64_t* pv_done = bars + 21;    // [g*2 + b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * A2_BM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = (ntok + AT_BN - 1) / AT_BN;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < A2_KVSTAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, A2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_QTILE);
+      tma_load_3d(smem + A2_OFF_Q, &mapQ, q_full, head * 64, q0, b);   // 256 rows: tile g at + g * 16 KB
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * AT_KTILE);
+        tma_load_3d(smem + A2_OFF_K + st * AT_KTILE, &mapK, &kv_full[st], head * 64, j * AT_BN, b);
+        tma_load_3d(smem + A2_OFF_V + st * AT_KTILE, &mapV, &kv_full[st], head * 64, j * AT_BN, b);
+        if (++st == A2_KVSTAGES) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+      auto issue_s = [&](int g, int j, int st) {
+        const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + A2_OFF_Q + g * AT_QTILE));
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + A2_OFF_K + st * AT_KTILE));
+        const uint32_t d_s = tmem_base + static_cast<uint32_t>(g * 128 + (j & 1) * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(d_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
+        tc_commit(&s_full[g * 2 + (j & 1)]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0, 0);
+      issue_s(1, 0, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        int st1 = st + 1;
+        uint32_t ph1 = ph;
+        if (st1 == A2_KVSTAGES) {
+          st1 = 0;
+          ph1 ^= 1u;
+        }
+        if (j + 1 < nkv) {
+          mbar_wait(&kv_full[st1], ph1);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            // S[g][(j+1)&1] is free once group g holds the scores of tile j-1 in registers
+            mbar_wait(&s_empty[g * 2 + ((j + 1) & 1)], (((j + 1) >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            issue_s(g, j + 1, st1);
+          }
+        }
+        const uint32_t vbase = smem_u32(smem + A2_OFF_V + st * AT_KTILE);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_ready[g * 2 + (j & 1)], (j >> 1) & 1);
+          tc_fence_after();
+          const uint64_t dp0 = umma_desc_k_sw128(smem_u32(smem + A2_OFF_P + (g * 2 + (j & 1)) * AT_QTILE));
+          const uint32_t t_o = tmem_base + 256u + static_cast<uint32_t>(g * 64);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dv = umma_desc_mn_sw128(vbase + kk * 2048, AT_KTILE);
+            tc_mma_f16(t_o, dp0 + static_cast<uint64_t>(2 * kk), dv, idesc_pv, (j | kk) != 0);
+          }
+          tc_commit(&pv_done[g * 2 + (j & 1)]);
+        }
+        tc_commit(&kv_empty[st]);
+        st = st1;
+        ph = ph1;
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;          // query tile of this softmax group
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane;            // row inside the tile
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + static_cast<uint32_t>(g * 128);
+    const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(g * 64);
+    uint64_t* sf = s_full + g * 2;
+    uint64_t* se = s_empty + g * 2;
+    uint64_t* pr = p_ready + g * 2;
+    uint64_t* pd = pv_done + g * 2;
+    const int sw = r & 7;
+    float m_ref = -INFINITY, l_run = 0.f;
+    const uint64_t sl2 = pack2(scale_log2e, scale_log2e);
+    uint32_t sa[64], sb_[64];
+
+    auto load_scores = [&](int j, uint32_t* dst) {   // asynchronous: tmem_ld_wait() before the first use
+      tmem_ld32p(tS + lane_base + static_cast<uint32_t>((j & 1) * 64), dst);
+      tmem_ld32p(tS + lane_base + static_cast<uint32_t>((j & 1) * 64 + 32), dst + 32);
+    };
+
+    // tile j from `cur` (already in registers); the scores of tile j+1 are requested into `nxt` in the middle
+    auto softmax_tile = [&](int j, uint32_t* cur, uint32_t* nxt, auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
+      const int kbase = j * AT_BN;
+      const int pb = j & 1;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        float a0 = __uint_as_float(cur[i]), a1 = __uint_as_float(cur[i + 1]);
+        if (TAIL) {
+          if (kbase + i >= ntok) a0 = -INFINITY;
+          if (kbase + i + 1 >= ntok) a1 = -INFINITY;
+        }
+        mx4[(i >> 1) & 3] = fmaxf(fmaxf(a0, a1), mx4[(i >> 1) & 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool need = (mx - m_ref) * scale_log2e > AT_RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          float fac = 1.0f;
+          if (need) {
+            fac = ex2_approx((m_ref - mx) * scale_log2e);
+            m_ref = mx;
+          }
+          l_run *= fac;
+          mbar_wait(&pd[(j - 1) & 1], ((j - 1) >> 1) & 1);  // O holds tiles 0..j-1
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld16p(tO + lane_base + static_cast<uint32_t>(c * 16), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * fac);
+            tmem_st16p(tO + lane_base + static_cast<uint32_t>(c * 16), o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // next tile's scores: S_{j+1} was issued before P_j V_j, so it is normally complete by now
+      if (j + 1 < nkv) {
+        mbar_wait(&sf[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        load_scores(j + 1, nxt);
+      }
+      if (j >= 2) mbar_wait(&pd[pb], ((j - 2) >> 1) & 1);   // P[g][pb] was last read by P_{j-2} V_{j-2}
+      const float msc = m_ref * scale_log2e;
+      const uint64_t nm2 = pack2(-msc, -msc);
+      uint64_t lsum = 0ull;
+      uint8_t* prow = smem + A2_OFF_P + (g * 2 + pb) * AT_QTILE + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const int i = c * 8 + e;
+          float x0, x1;
+          unpack2(fma2(pack2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2, nm2), x0, x1);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          if (TAIL) {
+            if (kbase + i >= ntok) p0 = 0.f;
+            if (kbase + i + 1 >= ntok) p1 = 0.f;
+          }
+          lsum = add2(lsum, pack2(p0, p1));
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+        }
+        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      float l0, l1;
+      unpack2(lsum, l0, l1);
+      l_run += l0 + l1;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&pr[pb]);
+      if (j + 1 < nkv) {
+        tmem_ld_wait();             // `nxt` is valid from here on
+        tc_fence_before();
+        mbar_arrive(&se[(j + 1) & 1]);
+      }
+    };
+
+    mbar_wait(&sf[0], 0);
+    tc_fence_after();
+    load_scores(0, sa);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&se[0]);
+    for (int j = 0; j < nkv; j += 2) {
+      if (j * AT_BN + AT_BN > ntok) softmax_tile(j, sa, sb_, std::true_type{});
+      else softmax_tile(j, sa, sb_, std::false_type{});
+      if (j + 1 < nkv) {
+        if ((j + 1) * AT_BN + AT_BN > ntok) softmax_tile(j + 1, sb_, sa, std::true_type{});
+        else softmax_tile(j + 1, sb_, sa, std::false_type{});
+      }
+    }
+    {
+      const int pj = nkv - 1;
+      mbar_wait(&pd[pj & 1], (pj >> 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      const int row = q0 + g * AT_BM + r;
+      bf16* op = O + (static_cast<long long>(b) * ntok + row) * ldo + head * 64;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t v[32];
+        tmem_ld32p(tO + lane_base + static_cast<uint32_t>(c2 * 32), v);
+        tmem_ld_wait();
+        if (row < ntok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2)
+              w[e >> 1] = pack_bf16x2(__uint_as_float(v[i + e]) * inv, __uint_as_float(v[i + e + 1]) * inv);
+            *reinterpret_cast<uint4*>(op + c2 * 32 + i) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A2_TMEM_COLS);
+  }
+}
+
 }  // namespace v3d
 
 using namespace v3d;
@@ -357,6 +654,32 @@ int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, 
       return V3D_ERR_CUDA;
     }
     cfg[poly] = true;
+  }
+  // V3D_ATTN_TILES = 2 (default) | 1: two query tiles per CTA with pipelined score loads (attn_tc2_kernel) for
+  // sequences of at least 256 tokens; 1 = the one-tile kernel everywhere
+  static int tiles = -1;
+  if (tiles < 0) {
+    const char* v = getenv("V3D_ATTN_TILES");
+    tiles = (v && atoi(v) == 1) ? 1 : 2;
+  }
+  if (tiles == 2 && ntok >= A2_BM && poly == 0) {
+    CUtensorMap mq2;
+    const uint32_t box_q2[3] = {64, A2_BM, 1};
+    if ((rc = make_tmap_bf16(&mq2, q, 3, dims, str, box_q2))) return rc;
+    static bool cfg2 = false;
+    if (!cfg2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+      if (e != cudaSuccess) {
+        set_error("attn_tc2 smem attr: %s", cudaGetErrorString(e));
+        return V3D_ERR_CUDA;
+      }
+      cfg2 = true;
+    }
+    dim3 grid2((ntok + A2_BM - 1) / A2_BM, nheads, nbatch);
+    attn_tc2_kernel<<<grid2, A2_THREADS, A2_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        mq2, mk, mv, static_cast<bf16*>(o), ld_o, ntok, scale * 1.44269504088896340736f);
+    V3D_CHECK_LAUNCH("attn_tc2_kernel");
+    return V3D_OK;
   }
   dim3 grid((ntok + AT_BM - 1) / AT_BM, nheads, nbatch);
   kerns[poly]<<<grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(

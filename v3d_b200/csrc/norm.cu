@@ -184,7 +184,10 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(512)
+// MAXT / MINB: launch bounds.  <256, 3> (80 registers) is what every width up to C = 2048 uses: three 240-256-thread
+// CTAs per SM instead of two keep enough loads in flight for the streaming phases; wider rows take <512, 1>.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 gn_fused_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                 const float* __restrict__ beta, GnBarrier* __restrict__ bar, float2* __restrict__ partial,
                 long long rows_per_sample, int C, long long ldx, int groups, float eps, int silu, int rows_per_cta) {
@@ -726,7 +729,8 @@ int v3d_groupnorm(const void* x, void* y, const void* gamma, const void* beta, i
   const size_t smem = sizeof(float) * 2 * static_cast<size_t>(lanes_r) * C;
   // co-resident capacity of this launch shape (the barrier needs every CTA on the device at once)
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
+  auto kern = threads <= 256 ? gn_fused_kernel<256, 3> : gn_fused_kernel<512, 1>;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
   if (e != cudaSuccess || per_sm < 1) {
     set_error("v3d_groupnorm: occupancy query failed (%s)", cudaGetErrorString(e));
     return V3D_ERR_CUDA;
@@ -747,7 +751,7 @@ int v3d_groupnorm(const void* x, void* y, const void* gamma, const void* beta, i
   chunks = (rows_per_sample + rpc - 1) / rpc;
   dim3 grid(static_cast<unsigned>(chunks), nsamples);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  gn_fused_kernel<<<grid, threads, smem, st>>>(
+  kern<<<grid, threads, smem, st>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(y), static_cast<const float*>(gamma),
       static_cast<const float*>(beta), reinterpret_cast<GnBarrier*>(ws), reinterpret_cast<float2*>(ws + 256),
       rows_per_sample, C, ldx, groups, eps, silu, static_cast<int>(rpc));
