@@ -18,7 +18,7 @@ from pathlib import Path
 
 import torch
 
-from . import ref_conditioning, ref_decoder, ref_encoder, ref_sampling, ref_unet, reference_shim, synth
+from . import ref_clip, ref_conditioning, ref_decoder, ref_encoder, ref_sampling, ref_unet, reference_shim, synth
 
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 PIN_TOL = 2e-4
@@ -197,6 +197,35 @@ def _encoder_case(ns, tag: str, ch: int, B: int, hw: int, wseed: int, manifest: 
                          out_std=ref.std().item())
 
 
+def _clip_case(tag: str, spec: "ref_clip.ClipSpec", B: int, img_hw: int, wseed: int, manifest: dict):
+    """the CLIP ViT-H/14 image tower.  open_clip (the reference's dependency) is absent offline, so the
+    stored output comes from an INDEPENDENT implementation of the same architecture - Hugging Face transformers'
+    CLIPVisionModelWithProjection - on the per-name seeded weights; the oracle must reproduce it.  The image is
+    regenerated from its seed in the tests (torch CPU generator), only a subsample of the preprocessed image is kept."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+
+    sd = synth.synth_state_dict(ref_clip.clip_visual_param_shapes(spec), seed=wseed)
+    cfg = CLIPVisionConfig(hidden_size=spec.width, intermediate_size=spec.mlp, projection_dim=spec.embed_dim,
+                           num_hidden_layers=spec.layers, num_attention_heads=spec.heads, image_size=spec.image_size,
+                           patch_size=spec.patch, hidden_act="gelu", layer_norm_eps=1e-5, attention_dropout=0.0)
+    hf = CLIPVisionModelWithProjection(cfg).eval()
+    missing, unexpected = hf.load_state_dict(ref_clip.to_hf_state_dict(sd, spec), strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    g = torch.Generator().manual_seed(80)
+    x = torch.rand(B, 3, img_hw, img_hw, generator=g) * 2.0 - 1.0
+    pre = ref_clip.preprocess(x, spec.image_size)
+    with torch.no_grad():
+        ref = hf(pixel_values=pre).image_embeds
+        ora = ref_clip.clip_visual_forward(sd, spec, pre)
+    err = _pin(tag, ref, ora)
+    torch.save({"out": ref, "pre_sub": pre[:, :, ::4, ::4].clone()}, OUT / f"{tag}.pt")
+    manifest[tag] = dict(kind="clip_image_tower", B=B, image_hw=img_hw, x_seed=80, weight_seed=wseed, pin_err=err,
+                         out_std=ref.std().item(), spec=dict(image_size=spec.image_size, patch=spec.patch,
+                                                             width=spec.width, layers=spec.layers, heads=spec.heads,
+                                                             mlp=spec.mlp, embed_dim=spec.embed_dim),
+                         checker="transformers.CLIPVisionModelWithProjection (independent implementation; open_clip absent)")
+
+
 def _conditioning_case(ns, tag: str, T: int, hw: int, manifest: dict):
     """(c, uc) of scripts/pub/V3D_512.py:247-262 through the real GeneralConditioner with the embedder
     list of scripts/pub/configs/V3D_512.yaml:59-86.  get_batch (V3D_512.py:31-69) lives in a script that cannot be
@@ -283,6 +312,11 @@ def main(argv):
         _encoder_case(ns, "encoder_small", 64, B=2, hw=64, wseed=7, manifest=manifest)
     if want("encoder_full"):
         _encoder_case(ns, "encoder_full", 128, B=1, hw=128, wseed=8, manifest=manifest)
+    if want("clip_small"):
+        _clip_case("clip_small", ref_clip.ClipSpec(image_size=56, patch=14, width=160, layers=2, heads=2, mlp=640,
+                                                   embed_dim=64), B=2, img_hw=96, wseed=21, manifest=manifest)
+    if want("clip_vit_h14"):
+        _clip_case("clip_vit_h14", ref_clip.ClipSpec(), B=1, img_hw=512, wseed=22, manifest=manifest)
     if want("conditioning"):
         _conditioning_case(ns, "conditioning", T=18, hw=8, manifest=manifest)
     # integer / index paths: sigma schedule and guider scale, bit-exact

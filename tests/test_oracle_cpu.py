@@ -134,3 +134,56 @@ def test_oracle_cfg_order_and_chunking():
         ref_halves = torch.cat([ref_decoder.decoder_forward(sd, spec, z[:2] / 0.18215, 2),
                                 ref_decoder.decoder_forward(sd, spec, z[2:] / 0.18215, 2)])
     assert torch.allclose(halves, ref_halves, atol=1e-5) and not torch.allclose(whole, halves, atol=1e-3)
+
+
+def test_clip_tower_oracle_matches_hf_transformers():
+    """open_clip (the reference's dependency for the ViT-H/14 image tower) is absent offline; the
+    oracle restatement (oracle/ref_clip.py) is pinned against an independent implementation of the same architecture,
+    Hugging Face transformers' CLIPVisionModelWithProjection, on per-name seeded weights mapped name by name."""
+    transformers = pytest.importorskip("transformers")
+    from oracle import ref_clip, synth
+
+    spec = ref_clip.ClipSpec(image_size=56, patch=14, width=128, layers=3, heads=2, mlp=512, embed_dim=96)
+    sd = synth.synth_state_dict(ref_clip.clip_visual_param_shapes(spec), seed=31)
+    cfg = transformers.CLIPVisionConfig(hidden_size=spec.width, intermediate_size=spec.mlp, projection_dim=spec.embed_dim,
+                                        num_hidden_layers=spec.layers, num_attention_heads=spec.heads,
+                                        image_size=spec.image_size, patch_size=spec.patch, hidden_act="gelu",
+                                        layer_norm_eps=1e-5, attention_dropout=0.0)
+    hf = transformers.CLIPVisionModelWithProjection(cfg).eval()
+    missing, unexpected = hf.load_state_dict(ref_clip.to_hf_state_dict(sd, spec), strict=False)
+    assert not missing and not unexpected
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(3, 3, 56, 56, generator=g)
+    with torch.no_grad():
+        ref = hf(pixel_values=img).image_embeds
+        ora = ref_clip.clip_visual_forward(sd, spec, img)
+    assert (ref - ora).abs().max() <= 2e-5 * ref.abs().max()
+
+
+def test_clip_oracle_reproduces_golden_and_preprocess_properties():
+    """The committed CLIP fixtures (outputs of the Hugging Face implementation) against the oracle, and closed-form
+    properties of the restated kornia resize: a constant image stays constant, the output is 224 x 224, a 224 x 224
+    input is only renormalised (no blur, identity interpolation)."""
+    from oracle import ref_clip, synth
+
+    m = MANIFEST["clip_small"]
+    gold = torch.load(GOLD / "clip_small.pt")
+    spec = ref_clip.ClipSpec(**m["spec"])
+    sd = synth.synth_state_dict(ref_clip.clip_visual_param_shapes(spec), seed=m["weight_seed"])
+    g = torch.Generator().manual_seed(m["x_seed"])
+    x = torch.rand(m["B"], 3, m["image_hw"], m["image_hw"], generator=g) * 2.0 - 1.0
+    pre = ref_clip.preprocess(x, spec.image_size)
+    assert torch.allclose(pre[:, :, ::4, ::4], gold["pre_sub"], atol=1e-6)
+    out = ref_clip.clip_visual_forward(sd, spec, pre)
+    assert (out - gold["out"]).abs().max() <= 2e-5 * gold["out"].abs().max()
+    emb = ref_clip.image_embedder_forward(sd, spec, x, n_cond_frames=1, n_copies=2)
+    assert emb.shape == (2 * m["B"], 1, spec.embed_dim) and torch.equal(emb[0], emb[1])
+    const = torch.full((1, 3, 300, 300), 0.25)
+    pc = ref_clip.preprocess(const)
+    assert pc.shape == (1, 3, 224, 224)
+    want = (0.625 - torch.tensor(ref_clip.CLIP_MEAN)) / torch.tensor(ref_clip.CLIP_STD)
+    assert torch.allclose(pc[0, :, 100, 100], want, atol=1e-5) and torch.allclose(pc[0, :, 0, 0], want, atol=1e-5)
+    same = torch.rand(1, 3, 224, 224) * 2 - 1
+    assert torch.allclose(ref_clip.preprocess(same),
+                          ((same + 1) / 2 - torch.tensor(ref_clip.CLIP_MEAN).view(1, 3, 1, 1)) /
+                          torch.tensor(ref_clip.CLIP_STD).view(1, 3, 1, 1), atol=1e-5)

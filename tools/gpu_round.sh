@@ -81,15 +81,20 @@ for stage in "$@"; do
     micro_all)
       run 600 micro_all.log $PY tools/microbench.py gemm conv attn norm small ;;
     viewshard2)
-      V3D_RUN_UNVALIDATED=1 run 600 viewshard_nccl.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "nccl"
-      run 900 bench_views2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 bench.py --gpus 2 --shard views --steps 3 --warmup 3
-      V3D_VIEWSHARD_GRAPH=1 run 900 bench_views2_graph.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
-        --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --shard views --steps 3 --warmup 3
-      run 900 bench_cfg2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29514 bench.py --gpus 2 --shard cfg --steps 3 --warmup 3
-      run 900 bench_images2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29513 bench.py --gpus 2 --steps 3 --warmup 3 ;;
+      # (2 GPUs) parity of the one-image-over-ranks plans (peer-memory transport by default over NCCL groups, then
+      # torch.distributed collectives), then throughput: image-parallel line with its `strong` sub-object (all plans),
+      # and the frame-sharded plan over NCCL collectives, eager and graph-captured, for comparison
+      run 900 viewshard_tests.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -x
+      run 900 bench_n2.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3
+      V3D_SHARD_TRANSPORT=nccl run 900 bench_views2_nccl.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+        --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --shard views --steps 2 --warmup 3 --no-parity
+      V3D_SHARD_TRANSPORT=nccl V3D_VIEWSHARD_GRAPH=1 run 900 bench_views2_nccl_graph.json $PY -m torch.distributed.run --nnodes=1 \
+        --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --shard views --steps 2 --warmup 3 --no-parity ;;
+    strongN)
+      # (N GPUs, N = $NGPU) the default line (image-parallel + `strong` sub-object)
+      run 900 bench_n${NGPU:-8}.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 \
+        --master-port 29521 bench.py --gpus ${NGPU:-8} --steps 3 --warmup 3 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

@@ -315,45 +315,56 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
 
 // ------------------------------------------------------------------------------------------------
-// Two query tiles per CTA (256 queries x one (sample, head)), ONE CTA per SM: the same dataflow as attn_tc_kernel with
-//   * two softmax groups of four warps (group g owns query tile g: its S double buffer, its P double buffer and its O
-//     accumulator in TMEM), sharing every K/V tile that TMA brings in (half the K/V traffic per query);
-//   * the scores of tile j+1 pulled from TMEM into a SECOND register set while the exponentials of tile j are computed
-//     (the 1-CTA/SM register budget pays for it), so the tcgen05.ld latency and the wait for the next QK^T sit under
-//     the MUFU stream instead of in front of it;
-//   * a tree row maximum (four independent FMNMX chains instead of one 32-deep chain).
-// The tensor pipe alternates S_0, S_1, P_0 V, P_1 V: while one group is in its exponentials the other group's MMAs run.
-// TMEM: S[g][b] at columns g*128 + b*64 (256), O[g] at 256 + g*64 (128): 384 of a 512-column allocation.
+// NG query tiles per CTA (NG x 128 queries x one (sample, head)), ONE CTA per SM.
+//
+// What the one-tile kernel leaves on the table (ncu, profiles/ncu_r2_set_baseline_raw.csv): the MUFU pipe - the unit
+// that bounds a head-dim-64 softmax, 16 ex2 per clock per SM - is busy 58 % of the time, the tensor pipe 29 %, and the
+// FMA-pipe exp2 variants are SLOWER (profiles/microbench_r2_pair_rtma.md): the limit is not a pipe but the number of
+// softmax warps.  Two CTAs per SM give each SM sub-partition two of them, and a warp spends about as long outside its
+// exponentials (tcgen05.ld, row maximum, fences, barrier waits) as inside.  Registers are per sub-partition (16 K), so
+// more softmax warps means fewer registers each: this kernel runs NG = 3 groups of four softmax warps (12 + the TMA
+// and MMA warps = 14 warps, <= 128 registers) so that three warps per sub-partition interleave on the MUFU pipe.
+//   * group g owns query tile g: its score buffer S[g] (single: S_g(j+1) is issued as soon as the group holds S_g(j)
+//     in registers and completes far inside the 512 MUFU cycles of the tile), its two P operand tiles and its O
+//     accumulator in TMEM;
+//   * every K/V tile TMA brings in is shared by the NG tiles (a third of the K/V shared-memory traffic per query);
+//   * the tensor pipe alternates S_g(j+1), P_g(j) V(j) group by group in the order the groups finish.
+// TMEM: S[g] at columns g*64, O[g] at NG*64 + g*64 (384 of a 512-column allocation for NG = 3).
 // ------------------------------------------------------------------------------------------------
-constexpr int A2_BM = 256;
-constexpr int A2_THREADS = 320;
 constexpr int A2_KVSTAGES = 4;
-constexpr int A2_OFF_Q = 0;                                          // 2 x 16 KB
-constexpr int A2_OFF_K = A2_OFF_Q + 2 * AT_QTILE;
-constexpr int A2_OFF_V = A2_OFF_K + A2_KVSTAGES * AT_KTILE;
-constexpr int A2_OFF_P = A2_OFF_V + A2_KVSTAGES * AT_KTILE;          // [g][b]: 4 x 16 KB
-constexpr int A2_OFF_BAR = A2_OFF_P + 4 * AT_QTILE;
-constexpr int A2_SMEM = A2_OFF_BAR + 512;
-constexpr uint32_t A2_TMEM_COLS = 512;
+template <int NG>
+struct A2 {
+  static constexpr int BM = NG * AT_BM;
+  static constexpr int THREADS = 64 + 128 * NG;
+  static constexpr int OFF_Q = 0;                                          // NG x 16 KB
+  static constexpr int OFF_K = OFF_Q + NG * AT_QTILE;
+  static constexpr int OFF_V = OFF_K + A2_KVSTAGES * AT_KTILE;
+  static constexpr int OFF_P = OFF_V + A2_KVSTAGES * AT_KTILE;             // [g][b]: 2 NG x 16 KB
+  static constexpr int OFF_BAR = OFF_P + 2 * NG * AT_QTILE;
+  static constexpr int SMEM = OFF_BAR + 512;
+  static constexpr uint32_t TMEM_COLS = 512;
+};
 
-__global__ void __maxnreg__(200)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+template <int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
+attn_tcg_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, bf16* __restrict__ O, long long ldo, int ntok,
                 float scale_log2e) {
+  using C = A2<NG>;
   extern __shared__ __align__(1024) uint8_t at_smem[];
   uint8_t* smem = at_smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [4]
-  uint64_t* kv_empty = bars + 5;    // [4]
-  uint64_t* s_full = bars + 9;      // [g*2 + b]
-  uint64_t* s_empty = bars + 13;    // [g*2 + b]  128 arrivals
-  uint64_t* p_ready = bars + 17;    // [g*2 + b]  128 arrivals
-  uint64_t* pv_done = bars + 21;    // [g*2 + b]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* kv_full = bars + 1;                 // [4]
+  uint64_t* kv_empty = bars + 5;                // [4]
+  uint64_t* s_full = bars + 9;                  // [g]
+  uint64_t* s_empty = s_full + NG;              // [g]          128 arrivals
+  uint64_t* p_ready = s_empty + NG;             // [g*2 + b]    128 arrivals
+  uint64_t* pv_done = p_ready + 2 * NG;         // [g*2 + b]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2 * NG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * A2_BM;
+  const int q0 = blockIdx.x * C::BM;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int nkv = (ntok + AT_BN - 1) / AT_BN;
@@ -368,16 +379,18 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NG; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
+    }
+    for (int i = 0; i < 2 * NG; ++i) {
       mbar_init(&p_ready[i], 128);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, A2_TMEM_COLS);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -387,15 +400,17 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * AT_QTILE);
-      tma_load_3d(smem + A2_OFF_Q, &mapQ, q_full, head * 64, q0, b);   // 256 rows: tile g at + g * 16 KB
+      mbar_arrive_expect_tx(q_full, NG * AT_QTILE);
+#pragma unroll
+      for (int g = 0; g < NG; ++g)   // one 128-row box per tile (rows past ntok are zero-filled)
+        tma_load_3d(smem + C::OFF_Q + g * AT_QTILE, &mapQ, q_full, head * 64, q0 + g * AT_BM, b);
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&kv_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&kv_full[st], 2 * AT_KTILE);
-        tma_load_3d(smem + A2_OFF_K + st * AT_KTILE, &mapK, &kv_full[st], head * 64, j * AT_BN, b);
-        tma_load_3d(smem + A2_OFF_V + st * AT_KTILE, &mapV, &kv_full[st], head * 64, j * AT_BN, b);
+        tma_load_3d(smem + C::OFF_K + st * AT_KTILE, &mapK, &kv_full[st], head * 64, j * AT_BN, b);
+        tma_load_3d(smem + C::OFF_V + st * AT_KTILE, &mapV, &kv_full[st], head * 64, j * AT_BN, b);
         if (++st == A2_KVSTAGES) {
           st = 0;
           ph ^= 1u;
@@ -406,20 +421,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int g, int j, int st) {
-        const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + A2_OFF_Q + g * AT_QTILE));
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + A2_OFF_K + st * AT_KTILE));
-        const uint32_t d_s = tmem_base + static_cast<uint32_t>(g * 128 + (j & 1) * 64);
+      auto issue_s = [&](int g, int st) {
+        const uint64_t dq = umma_desc_k_sw128(smem_u32(smem + C::OFF_Q + g * AT_QTILE));
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(smem + C::OFF_K + st * AT_KTILE));
+        const uint32_t d_s = tmem_base + static_cast<uint32_t>(g * 64);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           tc_mma_f16(d_s, dq + static_cast<uint64_t>(2 * k), dk + static_cast<uint64_t>(2 * k), idesc_s, k != 0);
-        tc_commit(&s_full[g * 2 + (j & 1)]);
+        tc_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0, 0);
-      issue_s(1, 0, 0);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) issue_s(g, 0);
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
@@ -429,23 +444,23 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
           st1 = 0;
           ph1 ^= 1u;
         }
-        if (j + 1 < nkv) {
-          mbar_wait(&kv_full[st1], ph1);
+        const bool more = j + 1 < nkv;
+        if (more) mbar_wait(&kv_full[st1], ph1);
+        const uint32_t vbase = smem_u32(smem + C::OFF_V + st * AT_KTILE);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            // S[g][(j+1)&1] is free once group g holds the scores of tile j-1 in registers
-            mbar_wait(&s_empty[g * 2 + ((j + 1) & 1)], (((j + 1) >> 1) & 1) ^ 1u);
-            tc_fence_after();
-            issue_s(g, j + 1, st1);
-          }
-        }
-        const uint32_t vbase = smem_u32(smem + A2_OFF_V + st * AT_KTILE);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < NG; ++g) {
+          // P_g(j) is written => the group also holds S_g(j) in registers: S[g] is free, and the group will come back
+          // for S_g(j+1) first, so that goes out before P_g(j) V(j)
           mbar_wait(&p_ready[g * 2 + (j & 1)], (j >> 1) & 1);
-          tc_fence_after();
-          const uint64_t dp0 = umma_desc_k_sw128(smem_u32(smem + A2_OFF_P + (g * 2 + (j & 1)) * AT_QTILE));
-          const uint32_t t_o = tmem_base + 256u + static_cast<uint32_t>(g * 64);
+          if (more) {
+            mbar_wait(&s_empty[g], j & 1);
+            tc_fence_after();
+            issue_s(g, st1);
+          } else {
+            tc_fence_after();
+          }
+          const uint64_t dp0 = umma_desc_k_sw128(smem_u32(smem + C::OFF_P + (g * 2 + (j & 1)) * AT_QTILE));
+          const uint32_t t_o = tmem_base + static_cast<uint32_t>(NG * 64 + g * 64);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t dv = umma_desc_mn_sw128(vbase + kk * 2048, AT_KTILE);
@@ -463,31 +478,31 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;            // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + static_cast<uint32_t>(g * 128);
-    const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(g * 64);
-    uint64_t* sf = s_full + g * 2;
-    uint64_t* se = s_empty + g * 2;
+    const uint32_t tS = tmem_base + static_cast<uint32_t>(g * 64);
+    const uint32_t tO = tmem_base + static_cast<uint32_t>(NG * 64 + g * 64);
     uint64_t* pr = p_ready + g * 2;
     uint64_t* pd = pv_done + g * 2;
     const int sw = r & 7;
     float m_ref = -INFINITY, l_run = 0.f;
     const uint64_t sl2 = pack2(scale_log2e, scale_log2e);
-    uint32_t sa[64], sb_[64];
+    // a tile of queries that lies entirely past ntok (last CTA of a sequence) still runs the protocol: its rows are
+    // zero-filled Q, and nothing is stored for them
 
-    auto load_scores = [&](int j, uint32_t* dst) {   // asynchronous: tmem_ld_wait() before the first use
-      tmem_ld32p(tS + lane_base + static_cast<uint32_t>((j & 1) * 64), dst);
-      tmem_ld32p(tS + lane_base + static_cast<uint32_t>((j & 1) * 64 + 32), dst + 32);
-    };
-
-    // tile j from `cur` (already in registers); the scores of tile j+1 are requested into `nxt` in the middle
-    auto softmax_tile = [&](int j, uint32_t* cur, uint32_t* nxt, auto tail_tag) {
+    auto softmax_tile = [&](int j, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
       const int kbase = j * AT_BN;
       const int pb = j & 1;
+      uint32_t s[64];
+      tmem_ld32p(tS + lane_base, s);
+      tmem_ld32p(tS + lane_base + 32u, s + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[g]);  // the scores live in registers: S[g] may take tile j+1
+      // ---- row maximum: four independent chains
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
-        float a0 = __uint_as_float(cur[i]), a1 = __uint_as_float(cur[i + 1]);
+        float a0 = __uint_as_float(s[i]), a1 = __uint_as_float(s[i + 1]);
         if (TAIL) {
           if (kbase + i >= ntok) a0 = -INFINITY;
           if (kbase + i + 1 >= ntok) a1 = -INFINITY;
@@ -520,17 +535,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
           tmem_st_wait();
         }
       }
-      // next tile's scores: S_{j+1} was issued before P_j V_j, so it is normally complete by now
-      if (j + 1 < nkv) {
-        mbar_wait(&sf[(j + 1) & 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        load_scores(j + 1, nxt);
-      }
-      if (j >= 2) mbar_wait(&pd[pb], ((j - 2) >> 1) & 1);   // P[g][pb] was last read by P_{j-2} V_{j-2}
+      if (j >= 2) mbar_wait(&pd[pb], ((j - 2) >> 1) & 1);   // P[g][pb] was last read by P_g(j-2) V(j-2)
       const float msc = m_ref * scale_log2e;
       const uint64_t nm2 = pack2(-msc, -msc);
       uint64_t lsum = 0ull;
-      uint8_t* prow = smem + A2_OFF_P + (g * 2 + pb) * AT_QTILE + r * 128;
+      uint8_t* prow = smem + C::OFF_P + (g * 2 + pb) * AT_QTILE + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint32_t pk[4];
@@ -538,7 +547,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         for (int e = 0; e < 8; e += 2) {
           const int i = c * 8 + e;
           float x0, x1;
-          unpack2(fma2(pack2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2, nm2), x0, x1);
+          unpack2(fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sl2, nm2), x0, x1);
           float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
           if (TAIL) {
             if (kbase + i >= ntok) p0 = 0.f;
@@ -555,26 +564,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&pr[pb]);
-      if (j + 1 < nkv) {
-        tmem_ld_wait();             // `nxt` is valid from here on
-        tc_fence_before();
-        mbar_arrive(&se[(j + 1) & 1]);
-      }
     };
 
-    mbar_wait(&sf[0], 0);
-    tc_fence_after();
-    load_scores(0, sa);
-    tmem_ld_wait();
-    tc_fence_before();
-    mbar_arrive(&se[0]);
-    for (int j = 0; j < nkv; j += 2) {
-      if (j * AT_BN + AT_BN > ntok) softmax_tile(j, sa, sb_, std::true_type{});
-      else softmax_tile(j, sa, sb_, std::false_type{});
-      if (j + 1 < nkv) {
-        if ((j + 1) * AT_BN + AT_BN > ntok) softmax_tile(j + 1, sb_, sa, std::true_type{});
-        else softmax_tile(j + 1, sb_, sa, std::false_type{});
-      }
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      if (j * AT_BN + AT_BN > ntok) softmax_tile(j, std::true_type{});
+      else softmax_tile(j, std::false_type{});
     }
     {
       const int pj = nkv - 1;
@@ -606,7 +602,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, A2_TMEM_COLS);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -655,30 +651,32 @@ int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, 
     }
     cfg[poly] = true;
   }
-  // V3D_ATTN_TILES = 2 (default) | 1: two query tiles per CTA with pipelined score loads (attn_tc2_kernel) for
-  // sequences of at least 256 tokens; 1 = the one-tile kernel everywhere
+  // V3D_ATTN_TILES = 3 (default) | 2 | 1: query tiles per CTA.  3 / 2 = attn_tcg_kernel<NG> (one CTA per SM, NG
+  // softmax groups) for sequences of at least NG * 128 tokens; 1 = the one-tile kernel (two CTAs per SM) everywhere
   static int tiles = -1;
   if (tiles < 0) {
     const char* v = getenv("V3D_ATTN_TILES");
-    tiles = (v && atoi(v) == 1) ? 1 : 2;
+    tiles = v ? atoi(v) : 3;
+    if (tiles < 1 || tiles > 3) tiles = 3;
   }
-  if (tiles == 2 && ntok >= A2_BM && poly == 0) {
-    CUtensorMap mq2;
-    const uint32_t box_q2[3] = {64, A2_BM, 1};
-    if ((rc = make_tmap_bf16(&mq2, q, 3, dims, str, box_q2))) return rc;
-    static bool cfg2 = false;
-    if (!cfg2) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+  if (tiles >= 2 && poly == 0 && ntok >= 2 * AT_BM) {
+    const int ng = (tiles == 3 && ntok >= 3 * AT_BM) ? 3 : 2;
+    using Kern2 = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, bf16*, long long, int, float);
+    const Kern2 k2 = ng == 3 ? static_cast<Kern2>(attn_tcg_kernel<3>) : static_cast<Kern2>(attn_tcg_kernel<2>);
+    const int smem2 = ng == 3 ? A2<3>::SMEM : A2<2>::SMEM;
+    static bool cfg2[4] = {false, false, false, false};
+    if (!cfg2[ng]) {
+      cudaError_t e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
       if (e != cudaSuccess) {
-        set_error("attn_tc2 smem attr: %s", cudaGetErrorString(e));
+        set_error("attn_tcg smem attr: %s", cudaGetErrorString(e));
         return V3D_ERR_CUDA;
       }
-      cfg2 = true;
+      cfg2[ng] = true;
     }
-    dim3 grid2((ntok + A2_BM - 1) / A2_BM, nheads, nbatch);
-    attn_tc2_kernel<<<grid2, A2_THREADS, A2_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        mq2, mk, mv, static_cast<bf16*>(o), ld_o, ntok, scale * 1.44269504088896340736f);
-    V3D_CHECK_LAUNCH("attn_tc2_kernel");
+    dim3 grid2((ntok + ng * AT_BM - 1) / (ng * AT_BM), nheads, nbatch);
+    k2<<<grid2, 64 + 128 * ng, smem2, static_cast<cudaStream_t>(stream)>>>(
+        mq, mk, mv, static_cast<bf16*>(o), ld_o, ntok, scale * 1.44269504088896340736f);
+    V3D_CHECK_LAUNCH("attn_tcg_kernel");
     return V3D_OK;
   }
   dim3 grid((ntok + AT_BM - 1) / AT_BM, nheads, nbatch);

@@ -744,7 +744,8 @@ int v3d_groupnorm(const void* x, void* y, const void* gamma, const void* beta, i
     return V3D_ERR_UNSUPPORTED;
   }
   long long chunks = cap / nsamples;
-  long long max_chunks = (rows_per_sample + 4LL * lanes_r - 1) / (4LL * lanes_r);  // >= 4 rows per thread
+  long long max_chunks = rows_per_sample / (16LL * lanes_r);  // >= 16 rows per thread: the barrier and the partials
+                                                              // must stay small next to the streaming loops
   if (max_chunks < 1) max_chunks = 1;
   if (chunks > max_chunks) chunks = max_chunks;
   long long rpc = (rows_per_sample + chunks - 1) / chunks;
@@ -780,7 +781,7 @@ int v3d_layernorm(const void* x, const void* add, void* ysum, void* y, const voi
     static int ln_ctas = 0;
     if (ln_ctas == 0) {
       const char* v = getenv("V3D_LN_CTAS_PER_SM");
-      ln_ctas = v ? atoi(v) : 16;
+      ln_ctas = v ? atoi(v) : 6;   // 6 resident-sized waves measured best on B200 (16: -5..10 %)
       if (ln_ctas < 1) ln_ctas = 1;
     }
     const long long cap2 = static_cast<long long>(ln_ctas) * num_sms();

@@ -181,7 +181,11 @@ class KernelModule(nn.Module):
     def _gn(self, P: dict, key: str, x: torch.Tensor, rows_per_sample: int, nsamples: int, c: int, eps: float,
             silu: bool) -> torch.Tensor:
         y = torch.empty(x.shape[0], c, device=x.device, dtype=torch.bfloat16)
-        if nsamples <= 256 and os.environ.get("V3D_GN_FUSED", "1") != "0":
+        # one launch (statistics -> grid barrier -> apply) where it measured faster than the statistics + apply pair:
+        # per-frame (2-D) norms whose tensor can still be re-read from the 126 MB L2 (-13..-23 % at the UNet's shapes);
+        # the 3-D time_stack norms (2 samples) and the decoder's GB-sized tensors stay on the pair
+        fused = 8 <= nsamples <= 256 and x.numel() * 2 <= 300e6
+        if fused and os.environ.get("V3D_GN_FUSED", "1") != "0":
             return ops.groupnorm(x, y, P[key + ".weight"], P[key + ".bias"], rows_per_sample, nsamples, c, eps, silu,
                                  self._gn_workspace(x.device))
         stats, pre_zeroed = self._take_stats(nsamples, x.device)
