@@ -651,13 +651,15 @@ int v3d_attention_spatial(const void* q, const void* k, const void* v, void* o, 
     }
     cfg[poly] = true;
   }
-  // V3D_ATTN_TILES = 3 (default) | 2 | 1: query tiles per CTA.  3 / 2 = attn_tcg_kernel<NG> (one CTA per SM, NG
-  // softmax groups) for sequences of at least NG * 128 tokens; 1 = the one-tile kernel (two CTAs per SM) everywhere
+  // V3D_ATTN_TILES = 1 (default) | 2 | 3: query tiles per CTA.  1 = the one-tile kernel, two CTAs per SM; 2 / 3 =
+  // attn_tcg_kernel<NG> (one CTA per SM, NG softmax groups sharing the K/V tiles) for sequences of at least NG * 128
+  // tokens - validated, but SLOWER on hardware (641 vs 531 / 571 TFLOP/s at 4096 tokens, profiles/microbench_r2_attn_norm.md):
+  // the softmax warps are bound by fixed-latency dependency stalls, not by the number of warps per sub-partition
   static int tiles = -1;
   if (tiles < 0) {
     const char* v = getenv("V3D_ATTN_TILES");
-    tiles = v ? atoi(v) : 3;
-    if (tiles < 1 || tiles > 3) tiles = 3;
+    tiles = v ? atoi(v) : 1;
+    if (tiles < 1 || tiles > 3) tiles = 1;
   }
   if (tiles >= 2 && poly == 0 && ntok >= 2 * AT_BM) {
     const int ng = (tiles == 3 && ntok >= 3 * AT_BM) ? 3 : 2;
