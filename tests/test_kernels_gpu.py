@@ -473,10 +473,8 @@ def test_sampler_arithmetic_and_u8():
     assert (u8.int() - ref.int()).abs().max() <= 1  # fp rounding of the *255 product may differ by one ulp
 
 
-# ---- opt-in kernel variants whose first hardware run is still pending: enabled with V3D_RUN_UNVALIDATED=1 (the
-# cta_group::2 tiles could hang the device on a cluster-barrier bug, so they only ever run in a child under a timeout)
-_unvalidated = pytest.mark.skipif(os.environ.get("V3D_RUN_UNVALIDATED") != "1",
-                                  reason="not yet run on hardware (set V3D_RUN_UNVALIDATED=1)")
+# ---- kernel variants that the default path selects per shape (V3D_GEMM_2CTA / V3D_GEMM_RTMA "auto"): the child processes
+# below force them onto EVERY eligible launch of the GEMM / conv tests of this file
 
 
 def test_heun_step_kernel():
@@ -497,20 +495,18 @@ def test_heun_step_kernel():
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
 
 
-@_unvalidated
 def test_gemm_cta_pair_path_subprocess():
-    """The cta_group::2 (CTA pair) GEMM tiles are opt-in (V3D_GEMM_2CTA=1, read once per process): re-run the GEMM /
-    conv tests of this file in a child process with the switch on, under a hard timeout."""
+    """The cta_group::2 (CTA pair) GEMM tiles (V3D_GEMM_2CTA, read once per process; default "auto" = per shape):
+    re-run the GEMM / conv tests of this file in a child process with the tiles forced on, under a hard timeout."""
     import subprocess
     import sys
 
-    env = dict(os.environ, V3D_GEMM_2CTA="1", V3D_RUN_UNVALIDATED="0")
+    env = dict(os.environ, V3D_GEMM_2CTA="1")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
                           "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
 
-@_unvalidated
 def test_gemm_tma_staged_residual_subprocess():
     """EPI_BF16RT (V3D_GEMM_RTMA=1, read once per process): the single residual of a bf16-output GEMM / conv arrives as
     128 x 32 TMA sub-tiles two sub-tiles ahead instead of per-lane global loads.  The GEMM / conv / temporal-conv tests
@@ -518,7 +514,7 @@ def test_gemm_tma_staged_residual_subprocess():
     import subprocess
     import sys
 
-    env = dict(os.environ, V3D_GEMM_RTMA="1", V3D_RUN_UNVALIDATED="0")
+    env = dict(os.environ, V3D_GEMM_RTMA="1")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
                           "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
@@ -534,7 +530,7 @@ def test_attention_poly_exp2_subprocess(poly):
     from pathlib import Path
 
     here = Path(__file__).resolve().parent
-    env = dict(os.environ, V3D_ATTN_POLY=str(poly), V3D_RUN_UNVALIDATED="0")
+    env = dict(os.environ, V3D_ATTN_POLY=str(poly))
     res = subprocess.run([sys.executable, "-m", "pytest", str(here / "test_kernels_gpu.py"),
                           str(here / "test_zz_attention_rescale_gpu.py"), "-x", "-q", "-m", "gpu", "-k",
                           "attention_spatial"], env=env, capture_output=True, text=True, timeout=600)

@@ -6,8 +6,7 @@
 #     gpurun --timeout 1200 -- 'bash tools/gpu_round.sh bench ncu_launches'
 #     gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_round.sh viewshard2'
 # Stages:
-#   tests         the validated GPU suite (pytest -m gpu; includes the first-run wrapper, which xfails on a child failure)
-#   firstrun      the not-yet-validated groups directly (V3D_RUN_UNVALIDATED=1), one child process each, verbose
+#   tests         the GPU suite (pytest -m gpu)
 #   pair          cta_group::2 GEMM tiles (V3D_GEMM_2CTA=1) under a 300 s timeout, then the per-shape microbenchmark
 #                 with the switch off / on
 #   rtma          TMA-staged residual epilogue (V3D_GEMM_RTMA=1): tests, then per-shape timings
@@ -33,30 +32,21 @@ for stage in "$@"; do
   case "$stage" in
     tests)
       run 1500 tests_gpu.log $PY -m pytest tests -m gpu -x -q ;;
-    firstrun)
-      export V3D_RUN_UNVALIDATED=1
-      run 300 first_kernels.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "heun_step_kernel or concat_timestep_embedder"
-      run 300 first_viewshard_kernels.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -k "halo_mode or split_kv"
-      run 600 first_viewshard_engine.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -k "one_gpu_gloo or single_rank"   # incl. the cfg / cfg+views plans
-      run 900 first_parity.log $PY -m pytest tests/test_parity_gpu.py -m gpu -q -s -k "encoder or heun or vanilla or central"
-      run 900 first_fullsize.log $PY -m pytest tests/test_fullsize_gpu.py -m gpu -q -s
-      run 300 first_standins.log $PY -m pytest tests/test_standins_gpu.py -m gpu -q
-      unset V3D_RUN_UNVALIDATED ;;
     pair)
       # the staged bring-up probe first: bounded waits, names the primitive that misbehaves instead of hanging
       [ -x tools/ubench/pair_min ] || nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr \
         -I include -I v3d_b200/csrc -o tools/ubench/pair_min tools/ubench/pair_min.cu v3d_b200/csrc/host_util.cu
       run 60 pair_probe.log tools/ubench/pair_min
-      V3D_RUN_UNVALIDATED=1 run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
+      run 300 pair_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "cta_pair"
       run 300 micro_single.log $PY tools/microbench.py gemm conv
       V3D_GEMM_2CTA=1 run 300 micro_pair.log $PY tools/microbench.py gemm conv ;;
     rtma)
       # TMA-staged residual epilogue (V3D_GEMM_RTMA=1): tests under a timeout (a barrier-phase mistake would hang),
       # then the per-shape microbenchmark with the switch off / on (the +R1 rows are the ones that should move)
-      V3D_RUN_UNVALIDATED=1 run 400 rtma_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "tma_staged_residual"
+      run 400 rtma_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "tma_staged_residual"
       V3D_GEMM_RTMA=1 run 300 micro_rtma.log $PY tools/microbench.py gemm conv ;;
     attn_poly)
-      V3D_RUN_UNVALIDATED=1 run 600 attn_poly_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "attention_poly_exp2"
+      run 600 attn_poly_tests.log $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -k "attention_poly_exp2"
       for k in 0 1 2 3; do V3D_ATTN_POLY=$k run 300 "micro_attn_poly$k.log" $PY tools/microbench.py attn; done ;;
     bench)
       run 900 bench.json $PY bench.py --steps 3 --warmup 3 ;;

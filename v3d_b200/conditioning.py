@@ -3,8 +3,8 @@
 (encoders/modules.py:85-206, 937-953) and the `get_batch` / per-frame repeat steps of scripts/pub/V3D_512.py:31-69,
 247-262.  Runs once per image; the only arithmetic is the sinusoidal embedding (`v3d_timestep_embedding`).
 
-Status: oracle pinned bit-exactly against the real GeneralConditioner (tests/golden/conditioning.pt); host logic
-tested on CPU; the device run is gated until it has been seen on a B200 (V3D_RUN_UNVALIDATED=1).
+Oracle pinned bit-exactly against the real GeneralConditioner (tests/golden/conditioning.pt); host logic tested on CPU,
+the device path in tests/test_kernels_gpu.py::test_concat_timestep_embedder_device (green on B200).
 """
 from __future__ import annotations
 

@@ -8,8 +8,8 @@ stride-2 convs whose zero padding is bottom/right only (model.py:74-91).  Same c
 keys as the reference encoder; forward takes NCHW fp32 images in [-1, 1] and returns the NCHW fp32 moments
 [B, 2*z, H/8, W/8].
 
-Status: oracle restatement pinned against the real reference and golden fixtures committed (tests/golden/encoder_*);
-the device run is gated until it has been seen on a B200 (tests/test_parity_gpu.py, V3D_RUN_UNVALIDATED=1).
+Oracle restatement pinned against the real reference, golden fixtures under tests/golden/encoder_*; the device path is
+checked against them in tests/test_parity_gpu.py::test_encoder_matches_reference (green on B200).
 """
 from __future__ import annotations
 
