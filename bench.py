@@ -586,7 +586,24 @@ def measure_strong(args, eng, dev, rank, world, T, L) -> dict:
             ops.frames_nchw_to_u8(img.contiguous(), u8)
             return plan.gather_frames(u8)
 
-        step()
+        # a plan that fails (an exchange that times out raises in sample_views on the rank that saw it) is reported
+        # and skipped on EVERY rank: the ranks agree on the outcome before anything is timed
+        ok, err = 1.0, ""
+        os.environ["V3D_PEER_CHECK"] = "0"      # no rank may leave the collective sequence early: checked below
+        try:
+            step()
+            torch.cuda.synchronize()
+            plan.check_status()
+        except Exception as exc:  # noqa: BLE001
+            ok, err = 0.0, f"{type(exc).__name__}: {exc}"[:300]
+        finally:
+            os.environ.pop("V3D_PEER_CHECK", None)
+        flag = torch.tensor([ok], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if flag.item() < 1.0:
+            out["plans"][mode] = {"error": err if ok == 0.0 else "failed on another rank"}
+            continue
         parallel.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -611,10 +628,12 @@ def measure_strong(args, eng, dev, rank, world, T, L) -> dict:
             unet.cuda_graphs = graphs_were
             restore()
         out["plans"][mode] = {"value": T * k / secs, "ms_per_image": 1000.0 * secs / k,
+                              "transport": plan.describe().get("transport"),
                               "blocks": plan.describe().get("sample_blocks") or plan.describe().get("decode_blocks"),
                               "exchanges_ms_per_image": summarise_exchanges(events, p0.elapsed_time(p1))}
-    if out["plans"]:
-        best = max(out["plans"], key=lambda m: out["plans"][m]["value"])
+    good = {m: v for m, v in out["plans"].items() if "value" in v}
+    if good:
+        best = max(good, key=lambda m: good[m]["value"])
         out["best_plan"] = best
         out["value"] = out["plans"][best]["value"]
         out["ms_per_image"] = out["plans"][best]["ms_per_image"]

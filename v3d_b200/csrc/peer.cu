@@ -15,7 +15,7 @@
 //                        (every rank gets bit-identical sums), times `scale`.
 //
 // The epoch is a device word that a one-thread kernel increments at the start of every sharded forward pass, so a
-// captured graph replays with fresh flag values.  Waits are bounded (about 20 s): a rank that never gets its signal
+// captured graph replays with fresh flag values.  Waits are bounded (5 s, and only the first one of a failed transport): a rank that never gets its signal
 // records the site in a status word and carries on instead of hanging the device; the host checks the status word.
 #include <cstring>
 
@@ -47,7 +47,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long kWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kWaitLimitNs = 5ull * 1000ull * 1000ull * 1000ull;
+// once one wait of a transport has timed out, every later wait falls through at once (the image is invalid anyway):
+// a broken exchange costs one time limit, not one per site
+__device__ __forceinline__ bool peer_failed(const unsigned int* status) {
+  return (*reinterpret_cast<const volatile unsigned int*>(status) & 0x80000000u) != 0u;
+}
 
 __global__ void peer_epoch_kernel(unsigned int* epoch) { *epoch += 1u; }
 
@@ -102,6 +107,7 @@ __global__ void peer_wait_kernel(const __grid_constant__ PeerWaitArgs a, const u
   // signed distance: robust against the 32-bit epoch wrapping
   while (static_cast<int>(ld_acquire_sys(f) - e) < 0) {
     __nanosleep(100);
+    if (peer_failed(status)) return;
     if (global_ns() - t0 > kWaitLimitNs) {
       atomicExch(status, 0x80000000u | static_cast<unsigned int>(a.site));
       return;
@@ -135,6 +141,7 @@ peer_allreduce_f64_kernel(const __grid_constant__ PeerReduceArgs a, double* __re
     const unsigned long long t0 = global_ns();
     while (static_cast<int>(ld_acquire_sys(f) - e) < 0) {
       __nanosleep(100);
+      if (peer_failed(status)) break;
       if (global_ns() - t0 > kWaitLimitNs) {
         atomicExch(status, 0x80000000u | static_cast<unsigned int>(a.site));
         break;
