@@ -87,6 +87,15 @@ typedef struct v3d_gemm_args {
    * a_rows = rows_per_batch + 2 * tap_shift): the neighbours' boundary frames of video_model.py:42-55 /
    * temporal_ae.py:94-99 when the T view-frames are split across GPUs. */
   int32_t a_rows, a_row0;
+  /* fused GEMM -> all-gather over peer memory (plain linear GEMMs with bf16 output; kv_n = 0: off).  Output columns
+   * >= kv_col0 are ALSO stored - by the same epilogue, with the same TMA sub-tile stores - into kv_n destination matrices
+   * kv_dst[i] (row stride kv_ld elements, column c - kv_col0, row = the output row), which may be IPC-mapped memory of
+   * other GPUs (v3d_peer_import): the frame-sharded temporal attention's K|V all-gather (video_attention.py:114-125
+   * around attention.py:337-341) leaves the projection GEMM tile by tile over NVLink instead of through a packing copy
+   * and a separate collective.  kv_col0 must be a multiple of 32. */
+  int32_t kv_col0, kv_n;
+  int64_t kv_ld;
+  void* kv_dst[8];
 } v3d_gemm_args;
 
 int v3d_gemm_bf16(const v3d_gemm_args* args, void* stream);

@@ -29,8 +29,11 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
     assert lib.v3d_abi_version() == 1
-    # the ctypes mirror of v3d_gemm_args: 7 pointers, 8 int64, 16 int32, 3 floats, 2 int32 (halo fields), padded to 8
-    assert ctypes.sizeof(_lib.GemmArgs) == (7 * 8 + 8 * 8 + 16 * 4 + 3 * 4 + 2 * 4 + 7) // 8 * 8
+    # the ctypes mirror of v3d_gemm_args: 7 pointers, 8 int64, 16 int32, 3 floats, 2 int32 (halo fields), padded to 8,
+    # then the fused K|V scatter block: 2 int32, 1 int64, 8 pointers
+    base = (7 * 8 + 8 * 8 + 16 * 4 + 3 * 4 + 2 * 4 + 7) // 8 * 8
+    assert ctypes.sizeof(_lib.GemmArgs) == base + 2 * 4 + 8 + 8 * 8
+    assert ctypes.sizeof(_lib.GemmArgs) == lib.v3d_gemm_args_size()
     assert lib.v3d_gemm_args_size() == ctypes.sizeof(_lib.GemmArgs)   # what the C side was compiled with
 
 
@@ -379,7 +382,7 @@ def test_schedule_cost_accounting_matches_known_flop_budget():
     tf = lambda book: sum(v[1] for v in book.values()) / 1e12          # noqa: E731
     assert 43.0 < tf(full["unet_forward"]) < 45.68                       # 45.68 TF reference accounting, minus 1.94 TF
     assert abs(tf(full["decode"]) - 54.77) < 0.5                         # decoder: nothing is skipped
-    assert full["unet_forward"]["gemm.conv3x3"][0] == 48 and full["unet_forward"]["groupnorm"][0] == 105  # one launch per norm
+    assert full["unet_forward"]["gemm.conv3x3"][0] == 48 and full["unet_forward"]["groupnorm"][0] == 61 and full["unet_forward"]["groupnorm_apply"][0] == 44  # per-frame norms: one launch; 3-D norms: the pair
     cfg = sc.run(18, 64, "cfg", 2, 0, 25)
     assert abs(tf(cfg["unet_forward"]) / tf(full["unet_forward"]) - 0.5) < 0.01
     assert cfg["comm_per_unet_forward"]["cfg_gather"] == [1, 18 * 4 * 64 * 64 * 4]

@@ -116,6 +116,30 @@ def test_single_rank_view_shard_equals_unsharded_engine():
     assert torch.isfinite(one).all() and r <= 3e-2, r      # fp64-atomic statistics order is the only difference
 
 
+@pytest.mark.parametrize("M,K,C", [(1000, 320, 320), (16384, 640, 640), (4608, 1280, 1280)])
+def test_gemm_kv_scatter_equals_output_columns(M, K, C):
+    """Fused projection GEMM -> all-gather: the epilogue stores the K|V columns (>= C of the packed q|k|v output) a second
+    time into every destination matrix - here two local buffers, one with a wider row stride; across GPUs the same
+    stores go to IPC-mapped peer memory.  The copies must be bit-identical to the output columns, the output itself
+    unchanged, rows past M untouched (one-CTA and, at M >= 8192, CTA-pair tiles)."""
+    from v3d_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3 * C, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(3 * C, device=DEV, generator=g)
+    ref = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, ref, K=K, N=3 * C, rows_per_batch=M, bias=bias)
+    out = torch.empty_like(ref)
+    d0 = torch.full((M + 64, 2 * C), 7.0, device=DEV, dtype=torch.bfloat16)
+    d1 = torch.full((M + 64, 2 * C), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, K=K, N=3 * C, rows_per_batch=M, bias=bias, kv=(C, [d0.data_ptr(), d1.data_ptr()], 2 * C))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    for d in (d0, d1):
+        assert torch.equal(d[:M], ref[:, C:]) and (d[M:] == 7.0).all()
+
+
 # --------------------------------------------------------------------------------------------------------------
 # model level
 # --------------------------------------------------------------------------------------------------------------

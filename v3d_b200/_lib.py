@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("out_transposed", C.c_int32), ("valid_cols", C.c_int32), ("accumulate", C.c_int32),
         ("s0", C.c_float), ("s1", C.c_float), ("s2", C.c_float),
         ("a_rows", C.c_int32), ("a_row0", C.c_int32),
+        ("kv_col0", C.c_int32), ("kv_n", C.c_int32), ("kv_ld", C.c_int64), ("kv_dst", C.c_void_p * 8),
     ]
 
 

@@ -46,6 +46,16 @@ struct GemmEpi {
   int tap0;  // A row coordinate of tap 0 relative to the output row: a_row0 - (ntaps / 2) * tap_shift
 };
 
+// Fused GEMM -> all-gather over peer memory: output sub-tiles whose first column is >= col0 are stored a second time
+// through each of these tensor maps (destination matrices that may live on other GPUs: IPC-mapped arenas), by the same
+// store leader with the same cp.async.bulk.tensor instruction.  n = 0: off (every launch but the frame-sharded K|V
+// projection).
+struct alignas(64) KvMaps {
+  CUtensorMap m[8];
+  int n;
+  int col0;
+};
+
 // Diagnostics (role timelines through v3d_debug_set_trace, V3D_GEMM_DEBUG stage-skipping switches) are compiled in
 // only with -DV3D_GEMM_DIAG: the hooks cost registers and ~6% of the epilogue's issue slots.
 #ifdef V3D_GEMM_DIAG
@@ -140,7 +150,8 @@ __device__ __forceinline__ void tile_origin(const GemmEpi& p, int m_tile, int& t
 template <int BN, bool CONV, int EPI, int NCTA = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapD, const GemmEpi p, const __grid_constant__ CUtensorMap mapR) {
+               const __grid_constant__ CUtensorMap mapD, const GemmEpi p, const __grid_constant__ CUtensorMap mapR,
+               const __grid_constant__ KvMaps kv) {
   constexpr bool RTMA = EPI == EPI_BF16RT;
   static_assert(!RTMA || NCTA == 1, "the TMA-staged residual variant is single-CTA");
   using C = Cfg<BN, NCTA, RTMA>;
@@ -649,6 +660,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   const int col0 = obase + c - (CPS - 1) * 16;
                   if (CONV) tma_store_4d(&mapD, src, col0, t0, t1, t2);
                   else tma_store_3d(&mapD, src, col0, t1, t0);
+                  if (!CONV && EPI == EPI_BF16 && kv.n > 0 && col0 >= kv.col0) {
+                    // fused all-gather: the same sub-tile into every rank's gather buffer (peer memory over NVLink)
+                    for (int i = 0; i < kv.n; ++i) tma_store_3d(&kv.m[i], src, col0 - kv.col0, t1, t0);
+                  }
                   bulk_commit();
                 }
                 V3D_ETRACE();  // sub-tile handed to TMA
@@ -715,6 +730,9 @@ static int pick_block_n(int N, int act) {
   return 0;
 }
 
+static KvMaps g_kv_none;  // zero-initialised: n = 0
+static const KvMaps* g_kv = &g_kv_none;  // set by v3d_gemm_bf16 around the one launch that scatters K|V
+
 template <int BN, bool CONV, int EPI, int NCTA = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmEpi& epi,
                   cudaStream_t st, const CUtensorMap* mr = nullptr) {
@@ -733,7 +751,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   if (NCTA == 1) {
     const int total = epi.num_m_tiles * epi.num_n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi, mres);
+    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(ma, mb, md, epi, mres, *g_kv);
   } else {
     // one cluster of two CTAs per 256-row pair tile, persistent over at most num_sms / 2 clusters
     const int total = ((epi.num_m_tiles + 1) / 2) * epi.num_n_tiles;
@@ -751,7 +769,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, epi, mres);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, md, epi, mres, *g_kv);
     if (e != cudaSuccess) {
       set_error("gemm_tc_kernel (CTA pair) launch failed: %s", cudaGetErrorString(e));
       return V3D_ERR_CUDA;
@@ -1143,6 +1161,33 @@ extern "C" int v3d_gemm_bf16(const v3d_gemm_args* a, void* stream) {
       if (rc) return rc;
     }
   }
-  return conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr)
-              : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr);
+  // fused GEMM -> all-gather (K|V scatter into peer memory): plain linear bf16-output launches only
+  KvMaps kvm;
+  memset(&kvm, 0, sizeof(kvm));
+  if (a->kv_n > 0) {
+    if (conv || ntaps != 1 || epi_kind != EPI_BF16 || a->batch > 1 || a->kv_n > 8 || a->kv_col0 <= 0 ||
+        a->kv_col0 % 32 != 0 || a->kv_col0 >= a->N || a->kv_ld < a->N - a->kv_col0 || a->kv_ld % 8 != 0 || bn % 32 != 0) {
+      set_error("v3d_gemm_bf16: K|V scatter needs a plain linear bf16 GEMM without a second residual (kv_col0=%d kv_n=%d "
+                "N=%d block_n=%d epilogue=%d)", a->kv_col0, a->kv_n, a->N, bn, epi_kind);
+      return V3D_ERR_BAD_ARG;
+    }
+    kvm.n = a->kv_n;
+    kvm.col0 = a->kv_col0;
+    const uint64_t dims[3] = {(uint64_t)(a->N - a->kv_col0), (uint64_t)e.rows_per_batch, 1};
+    const uint64_t str[2] = {(uint64_t)a->kv_ld * 2, (uint64_t)a->kv_ld * 2 * e.rows_per_batch};
+    const uint32_t box[3] = {32, BM, 1};
+    for (int i = 0; i < a->kv_n; ++i) {
+      if (a->kv_dst[i] == nullptr) {
+        set_error("v3d_gemm_bf16: kv_dst[%d] is null", i);
+        return V3D_ERR_BAD_ARG;
+      }
+      rc = make_tmap_bf16(&kvm.m[i], a->kv_dst[i], 3, dims, str, box, 64);
+      if (rc) return rc;
+    }
+    g_kv = &kvm;
+  }
+  rc = conv ? dispatch_bn<true>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr)
+            : dispatch_bn<false>(bn, epi_kind, ma, mb, md, e, st, pair, rtma ? &mr : nullptr);
+  g_kv = &g_kv_none;
+  return rc;
 }

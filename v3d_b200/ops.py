@@ -55,7 +55,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
          r1: Optional[torch.Tensor] = None, ldr1: int = 0, r2: Optional[torch.Tensor] = None, ldr2: int = 0,
          s0: float = 1.0, s1: float = 1.0, s2: float = 1.0, act: int = ACT_NONE, ntaps: int = 1,
          tap_shift: int = 0, conv: Optional[tuple] = None, block_n: int = 0, transposed: bool = False,
-         valid_cols: int = 0, accumulate: bool = False, a_rows: int = 0, a_row0: int = 0) -> torch.Tensor:
+         valid_cols: int = 0, accumulate: bool = False, a_rows: int = 0, a_row0: int = 0,
+         kv: Optional[tuple] = None) -> torch.Tensor:
     """General entry to v3d_gemm_bf16. `conv=(n, h, w)` selects the implicit 3x3 conv gather; `a_rows` / `a_row0`
     describe a halo'd A operand (frame-sharded temporal convs, see include/v3d_b200.h)."""
     _need(a, torch.bfloat16, "gemm A")
@@ -91,6 +92,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, K: int, N: int,
     g.accumulate = 1 if accumulate else 0
     g.s0, g.s1, g.s2 = s0, s1, s2
     g.a_rows, g.a_row0 = a_rows, a_row0
+    if kv is not None:
+        # fused GEMM -> all-gather: (first scattered column, [destination base addresses], destination row stride)
+        col0, dsts, ld = kv
+        g.kv_col0, g.kv_n, g.kv_ld = col0, len(dsts), ld
+        for i, d in enumerate(dsts):
+            g.kv_dst[i] = d
     _lib.check(_lib.load().v3d_gemm_bf16(C.byref(g), _stream()), "v3d_gemm_bf16")
     return out
 

@@ -839,8 +839,15 @@ class VideoUNet(KernelModule):
         g = self._linear(P, ts + ".ff_in.net.0.proj", a, rows, act=ops.ACT_GEGLU)
         self._linear(P, ts + ".ff_in.net.2", g, rows, out=xm, r1=xm, s1=1.0)
         a = ln(ts + ".norm1", xm)
-        qkv = self._linear(P, ts + ".attn1.qkv", a, rows, out=qkv)
         vs = self.view_shard
+        kv_buf = send = kv_dst = None
+        if vs is not None:
+            kv_buf, send = vs.kv_slots(nb, hw, 2 * c, torch.bfloat16, dev)
+            kv_dst = vs.kv_fused(kv_buf)
+        # frame-sharded over peer memory: the projection GEMM itself delivers its K|V columns into every rank's gather
+        # buffer (fused GEMM -> all-gather: the epilogue's TMA sub-tile stores go out once more per rank over NVLink)
+        qkv = self._linear(P, ts + ".attn1.qkv", a, rows, out=qkv,
+                           **({"kv": (c, kv_dst, 2 * c)} if kv_dst is not None else {}))
         if vs is None:
             ops.attention_temporal(qkv, o, nb, T, hw, heads, scale)
             # temporal cross-attention context = context[::T] (video_attention.py:250): row b*T of `cross`
@@ -848,11 +855,13 @@ class VideoUNet(KernelModule):
         else:
             # frame-sharded: all-gather the packed K|V rows of every rank's frames, attend in place through the
             # per-frame row table; the time context (global frame 0 of each CFG half) is rows B.. of `cross`
-            kv_buf, send = vs.kv_slots(nb, hw, 2 * c, torch.bfloat16, dev)
-            ops.copy_channels(qkv[:, c:], 3 * c, send, 2 * c, rows, 2 * c)
+            if kv_dst is not None:
+                gathered = vs.gather_signal(kv_buf)
+            else:
+                ops.copy_channels(qkv[:, c:], 3 * c, send, 2 * c, rows, 2 * c)
+                gathered = vs.gather_rows(send, kv_buf, rows)
             kv_row, kv_bstride = vs.kv_table(nb, hw)
-            ops.attention_temporal_kv(qkv, vs.gather_rows(send, kv_buf, rows), o, nb, T, hw, heads, kv_row,
-                                      kv_bstride, scale)
+            ops.attention_temporal_kv(qkv, gathered, o, nb, T, hw, heads, kv_row, kv_bstride, scale)
             tc_bias, tc_ld = cross[B:, ot:], X
         self._linear(P, ts + ".attn1.to_out.0", o, rows, out=xm, r1=xm, s1=1.0,
                      fbias=tc_bias, ldfb=tc_ld, rows_per_frame=T * hw)

@@ -248,6 +248,23 @@ class PeerTransport:
         self._wait([self._addr(st["flags"], self.rank, 4 * r) for r in range(self.world) if r != self.rank], st["id"])
         return buf
 
+    def kv_destinations(self, buf: torch.Tensor) -> List[int]:
+        """Address of THIS rank's slot in every rank's copy of the gather buffer (own arena included): the destination
+        matrices of the fused projection-GEMM -> all-gather (`ops.gemm(..., kv=...)`)."""
+        st = buf._v3d_site
+        block_rows = buf.shape[0] // self.world
+        slot = self.rank * block_rows * buf.shape[1] * buf.element_size()
+        return [self._addr(st["buf"], r, slot) for r in range(self.world)]
+
+    def gather_signal(self, buf: torch.Tensor) -> torch.Tensor:
+        """After a GEMM that scattered its K|V columns into every rank's buffer: raise this rank's flag on the peers
+        and wait for theirs (no data moves here)."""
+        st = buf._v3d_site
+        others = [r for r in range(self.world) if r != self.rank]
+        self._put([], [self._addr(st["flags"], r, 4 * self.rank) for r in others])
+        self._wait([self._addr(st["flags"], self.rank, 4 * r) for r in others], st["id"])
+        return buf
+
     def gather_halves(self, mine: torch.Tensor, parity: int) -> torch.Tensor:
         """CFG pair: [n, ...] per rank -> [2n, ...] on both (rank order).  `parity` alternates two sites."""
         nbytes = mine.numel() * mine.element_size()
@@ -439,6 +456,17 @@ class ViewShard:
         for dst, host in landing:
             dst.copy_(host)
         return pad
+
+    def kv_fused(self, buf: Optional[torch.Tensor]):
+        """None, or the destination addresses for the fused GEMM -> all-gather of the K|V projection (peer transport;
+        V3D_KV_FUSED=0 falls back to pack + put)"""
+        if buf is None or self.peer is None or os.environ.get("V3D_KV_FUSED", "1") == "0":
+            return None
+        return self.peer.kv_destinations(buf)
+
+    def gather_signal(self, buf: torch.Tensor) -> torch.Tensor:
+        self._count("kv_allgather")
+        return self.peer.gather_signal(buf)
 
     def gather_rows(self, send: torch.Tensor, buf: Optional[torch.Tensor] = None,
                     filled_rows: Optional[int] = None) -> torch.Tensor:
