@@ -90,7 +90,10 @@ def raw(path: str) -> None:
 
 def source(path: str, top: int = 25) -> None:
     rows = _rows(path)
-    head = rows[0]
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")      # skip the "Kernel Name" banner rows
+    if hi > 0 and rows[0] and rows[0][0] == "Kernel Name":
+        print(f"kernel: `{short_kernel(rows[0][1])}`\n")
+    head = rows[hi]
 
     def col(*subs):
         for i, h in enumerate(head):
@@ -103,17 +106,34 @@ def source(path: str, top: int = 25) -> None:
     iexec = col("instructions executed") or col("inst", "executed")
     if isrc is None or isamp is None:
         raise SystemExit(f"unexpected source-page columns: {head[:12]}")
-    data = []
-    for r in rows[1:]:
+    reasons = [(i, h) for i, h in enumerate(head) if h.startswith("stall_") and "Not Issued" not in h]
+    data, agg = [], defaultdict(int)
+    seen = set()
+    for r in rows[hi + 1:]:
+        if not r or not r[0].startswith("0x") or r[0] in seen:       # a second launch of the kernel repeats the listing
+            continue
+        seen.add(r[0])
         try:
-            data.append((int(float(r[isamp] or 0)), r[isrc].strip(), r[iexec] if iexec is not None else ""))
+            n = int(float(r[isamp] or 0))
         except (ValueError, IndexError):
             continue
+        why = []
+        for i, h in reasons:
+            try:
+                v = int(float(r[i] or 0))
+            except (ValueError, IndexError):
+                v = 0
+            agg[h] += v
+            if v:
+                why.append((v, h))
+        data.append((n, r[isrc].strip(), r[iexec] if iexec is not None else "", sorted(why, reverse=True)[:2]))
     total = sum(d[0] for d in data)
     print(f"warp-stall samples: {total}\n")
-    print("| samples | share | executed | SASS |\n|---|---|---|---|")
-    for s, src, ex in sorted(data, key=lambda d: -d[0])[:top]:
-        print(f"| {s} | {100 * s / max(total, 1):.1f}% | {ex} | `{src}` |")
+    print("stall reasons over the whole kernel: " +
+          ", ".join(f"{h[6:]} {100 * v / max(total, 1):.1f}%" for h, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v) + "\n")
+    print("| samples | share | executed | SASS | main reasons |\n|---|---|---|---|---|")
+    for n, src, ex, why in sorted(data, key=lambda d: -d[0])[:top]:
+        print(f"| {n} | {100 * n / max(total, 1):.1f}% | {ex} | `{src}` | {', '.join(f'{h[6:]} {v}' for v, h in why)} |")
 
 
 def traffic(path: str) -> None:
