@@ -152,7 +152,7 @@ def test_other_guiders_host_logic_bit_exact():
     assert torch.equal(g.scale, gold["central_scale_18"])
     assert torch.equal(sampling.CentralPredictionGuider(max_scale=2.5, num_frames=25).scale, gold["central_scale_25"])
     v = sampling.VanillaCFG(scale=2.5)
-    assert v.num_frames == 1 and v.scale_value == 2.5 and tuple(v.scale.shape) == (1, 1)
+    assert v.num_frames == 1 and v.scale_value == 2.5 and v.scale == 2.5 and isinstance(v.scale, float)
     v.scale = 4.0  # callers re-assign a python float (guiders.py:24-25)
     assert v.scale_value == 4.0
     c = {"vector": torch.ones(2, 3), "crossattn": torch.ones(2, 1, 2), "concat": torch.ones(2, 2, 2, 2)}

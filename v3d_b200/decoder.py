@@ -289,43 +289,45 @@ class VideoDecoder(KernelModule):
         dev, zc = z.device, self.z_channels
         n_norms = 4 * sum(1 for n, _, _ in self._blocks() if not n.startswith("@")) + 2
         object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
-        cur = torch.empty(B * H * W, zc, device=dev, dtype=torch.bfloat16)
-        ops.nchw_f32_to_nhwc_bf16(z.float().contiguous(), cur)
-        h, w = H, W
-        cur = self._conv3x3(P, "conv_in", cur, B, h, w, zc)
-        ch = self.ch * self.ch_mult[-1]
-        for name, ci, co in self._blocks():
-            if name.startswith("@attn:"):
-                if (h * w) % 64 != 0 or ci % 64 != 0:
-                    raise NotImplementedError("decoder AttnBlock needs h*w % 64 == 0")
-                cur = self._attn(P, name[6:], ci, cur, B, h, w)
-            elif name.startswith("@up:"):
-                up = torch.empty(B * 4 * h * w, ci, device=dev, dtype=torch.bfloat16)
-                ops.upsample_nearest2x(cur, up, B, h, w, ci)
-                h, w = 2 * h, 2 * w
-                cur = self._conv3x3(P, name[4:], up, B, h, w, ci)
-                del up
+        try:
+            cur = torch.empty(B * H * W, zc, device=dev, dtype=torch.bfloat16)
+            ops.nchw_f32_to_nhwc_bf16(z.float().contiguous(), cur)
+            h, w = H, W
+            cur = self._conv3x3(P, "conv_in", cur, B, h, w, zc)
+            ch = self.ch * self.ch_mult[-1]
+            for name, ci, co in self._blocks():
+                if name.startswith("@attn:"):
+                    if (h * w) % 64 != 0 or ci % 64 != 0:
+                        raise NotImplementedError("decoder AttnBlock needs h*w % 64 == 0")
+                    cur = self._attn(P, name[6:], ci, cur, B, h, w)
+                elif name.startswith("@up:"):
+                    up = torch.empty(B * 4 * h * w, ci, device=dev, dtype=torch.bfloat16)
+                    ops.upsample_nearest2x(cur, up, B, h, w, ci)
+                    h, w = 2 * h, 2 * w
+                    cur = self._conv3x3(P, name[4:], up, B, h, w, ci)
+                    del up
+                else:
+                    cur = self._video_res_block(P, name, ci, co, cur, B, T, nb, h, w)
+                    ch = co
+            a = self._gn(P, "norm_out", cur, h * w, B, ch, 1e-6, True)
+            if vs is None:
+                o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
+                out = torch.empty(B, self.out_ch, h, w, device=dev, dtype=torch.float32)
+                ops.time_mix_conv(o, o.shape[1], P["time_mix.weight"], P["time_mix.bias"], out, nb, T, h * w,
+                                  self.out_ch)
             else:
-                cur = self._video_res_block(P, name, ci, co, cur, B, T, nb, h, w)
-                ch = co
-        a = self._gn(P, "norm_out", cur, h * w, B, ch, 1e-6, True)
-        if vs is None:
-            o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
-            out = torch.empty(B, self.out_ch, h, w, device=dev, dtype=torch.float32)
-            ops.time_mix_conv(o, o.shape[1], P["time_mix.weight"], P["time_mix.bias"], out, nb, T, h * w,
-                              self.out_ch)
-        else:
-            # AE3DConv's time_mix_conv (temporal_ae.py:101-107) is one more (3,1,1) conv: conv_out lands in the
-            # interior of a halo'd fp32 buffer, the mix runs over T + 2 frames and the two halo frames are dropped
-            cop = P["conv_out.weight"].shape[0]
-            pad = vs.new_pad((1, T + 2, h * w, cop), torch.float32, dev)
-            self._conv3x3(P, "conv_out", a, B, h, w, ch, out=pad[0, 1:T + 1].view(B * h * w, cop))
-            vs.exchange_halos(pad)
-            full = torch.empty(T + 2, self.out_ch, h, w, device=dev, dtype=torch.float32)
-            ops.time_mix_conv(pad.view(-1, cop), cop, P["time_mix.weight"], P["time_mix.bias"], full, 1, T + 2,
-                              h * w, self.out_ch)
-            out = full[1:T + 1].contiguous()
-        object.__setattr__(self, "_gn_pool", None)
+                # AE3DConv's time_mix_conv (temporal_ae.py:101-107) is one more (3,1,1) conv: conv_out lands in the
+                # interior of a halo'd fp32 buffer, the mix runs over T + 2 frames and the two halo frames are dropped
+                cop = P["conv_out.weight"].shape[0]
+                pad = vs.new_pad((1, T + 2, h * w, cop), torch.float32, dev)
+                self._conv3x3(P, "conv_out", a, B, h, w, ch, out=pad[0, 1:T + 1].view(B * h * w, cop))
+                vs.exchange_halos(pad)
+                full = torch.empty(T + 2, self.out_ch, h, w, device=dev, dtype=torch.float32)
+                ops.time_mix_conv(pad.view(-1, cop), cop, P["time_mix.weight"], P["time_mix.bias"], full, 1, T + 2,
+                                  h * w, self.out_ch)
+                out = full[1:T + 1].contiguous()
+        finally:
+            object.__setattr__(self, "_gn_pool", None)   # also after a failed run (OOM mid-schedule)
         return out
 
 

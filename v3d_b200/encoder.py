@@ -205,26 +205,28 @@ class Encoder(KernelModule):
         dev = x.device
         n_norms = 2 * sum(1 for n, _, _ in self._blocks() if not n.startswith("@")) + 2
         object.__setattr__(self, "_gn_pool", [torch.zeros(n_norms * B * 64, device=dev, dtype=torch.float64), 0])
-        cur = torch.empty(B * H * W, cin, device=dev, dtype=torch.bfloat16)
-        ops.nchw_f32_to_nhwc_bf16(x.float().contiguous(), cur)
-        h, w = H, W
-        cur = self._conv3x3(P, "conv_in", cur, B, h, w, cin)
-        ch = self.ch
-        for name, ci, co in self._blocks():
-            if name.startswith("@attn:"):
-                if (h * w) % 64 != 0 or ci % 64 != 0:
-                    raise NotImplementedError("encoder AttnBlock needs h*w % 64 == 0")
-                cur = self._attn(P, name[6:], ci, cur, B, h, w)
-            elif name.startswith("@down:"):
-                cur, h, w = self._downsample(P, name[6:], cur, B, h, w, ci)
-            else:
-                cur = self._res_block(P, name, ci, co, cur, B, h, w)
-                ch = co
-        a = self._gn(P, "norm_out", cur, h * w, B, ch, 1e-6, True)
-        o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
-        out = torch.empty(B, self.out_channels, h, w, device=dev, dtype=torch.float32)
-        ops.nhwc_to_nchw_f32(o, out, B, self.out_channels, h * w, ldx=o.shape[1])
-        object.__setattr__(self, "_gn_pool", None)
+        try:
+            cur = torch.empty(B * H * W, cin, device=dev, dtype=torch.bfloat16)
+            ops.nchw_f32_to_nhwc_bf16(x.float().contiguous(), cur)
+            h, w = H, W
+            cur = self._conv3x3(P, "conv_in", cur, B, h, w, cin)
+            ch = self.ch
+            for name, ci, co in self._blocks():
+                if name.startswith("@attn:"):
+                    if (h * w) % 64 != 0 or ci % 64 != 0:
+                        raise NotImplementedError("encoder AttnBlock needs h*w % 64 == 0")
+                    cur = self._attn(P, name[6:], ci, cur, B, h, w)
+                elif name.startswith("@down:"):
+                    cur, h, w = self._downsample(P, name[6:], cur, B, h, w, ci)
+                else:
+                    cur = self._res_block(P, name, ci, co, cur, B, h, w)
+                    ch = co
+            a = self._gn(P, "norm_out", cur, h * w, B, ch, 1e-6, True)
+            o = self._conv3x3(P, "conv_out", a, B, h, w, ch, out_dtype=torch.float32)   # [rows, 16] fp32
+            out = torch.empty(B, self.out_channels, h, w, device=dev, dtype=torch.float32)
+            ops.nhwc_to_nchw_f32(o, out, B, self.out_channels, h * w, ldx=o.shape[1])
+        finally:
+            object.__setattr__(self, "_gn_pool", None)   # also after a failed run (OOM mid-schedule)
         return out
 
 

@@ -70,9 +70,15 @@ class _FrameScaleGuider:
 
     def _scale_on(self, device) -> torch.Tensor:
         # `self.scale` may be re-assigned by callers (scripts/pub/V3D_512.py:84-100); re-upload only when it changes
-        if self._scale_dev is None or self._scale_dev[0] is not self.scale or self._scale_dev[1].device != device:
-            self._scale_dev = (self.scale, self.scale.reshape(-1).float().to(device).contiguous())
+        # (re-assignment or an in-place edit such as `guider.scale[:, i] = ...`: the tensor's version counter moves)
+        scale = self._scale_tensor()
+        tag = (id(scale), scale._version)
+        if self._scale_dev is None or self._scale_dev[0] != tag or self._scale_dev[1].device != device:
+            self._scale_dev = (tag, scale.reshape(-1).float().to(device).contiguous())
         return self._scale_dev[1]
+
+    def _scale_tensor(self) -> torch.Tensor:
+        return self.scale
 
     def __call__(self, x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
         T = self.num_frames
@@ -128,9 +134,13 @@ class VanillaCFG(_FrameScaleGuider):
         self.scale_value = float(scale)
         self._init_keys(None)
 
-    # the reference keeps a python float in `.scale`; the device copy is derived from it on use
+    # the reference keeps a python float in `.scale` (guiders.py:24-25) and so does the attribute here; the [1, 1]
+    # tensor the combine kernel reads is derived from it
     @property
-    def scale(self):
+    def scale(self) -> float:
+        return float(self._scale_t.reshape(-1)[0])
+
+    def _scale_tensor(self) -> torch.Tensor:
         return self._scale_t
 
     @scale.setter

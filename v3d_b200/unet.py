@@ -58,15 +58,21 @@ def conv_tiles_ok(h: int, w: int) -> bool:
     return bw & (bw - 1) == 0 and bh & (bh - 1) == 0
 
 
+def _invalidate_after_load(module, incompatible_keys) -> None:
+    module._invalidate()
+
+
 class KernelModule(nn.Module):
     """Shared machinery: reference-named fp32 parameters + lazily packed kernel-side weights."""
 
     def __init__(self):
         super().__init__()
         self._packed: Optional[dict] = None
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        self.register_load_state_dict_post_hook(_invalidate_after_load)   # module-level function: picklable
 
     def _invalidate(self) -> None:
+        """Drop the packed bf16 weights and the captured CUDA graphs.  Called automatically by load_state_dict and
+        .to() / .cuda(); call it by hand after IN-PLACE edits of parameters (e.g. merging a LoRA with `p.data.add_`)."""
         self._packed = None
         if getattr(self, "_graphs", None):
             self._graphs.clear()  # captured graphs hold pointers into the old packed weights
@@ -671,7 +677,7 @@ class VideoUNet(KernelModule):
         -> ((x, timesteps, context rows, y) fp32 contiguous, (B, T, nb, H, W), use CUDA graphs)."""
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        assert y.shape[0] == x.shape[0]
+        assert y is None or y.shape[0] == x.shape[0]
         assert context is not None and context.ndim == 3, \
             f"n dims of spatial context should be 3 but are {None if context is None else context.ndim}"
         assert num_video_frames, "num_video_frames is required"
