@@ -503,7 +503,7 @@ def test_gemm_cta_pair_path_subprocess():
 
     env = dict(os.environ, V3D_GEMM_2CTA="1")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
-                          "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
+                          "(gemm or conv3x3 or temporal_conv) and not subprocess"], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
 
@@ -516,7 +516,7 @@ def test_gemm_tma_staged_residual_subprocess():
 
     env = dict(os.environ, V3D_GEMM_RTMA="1")
     res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k",
-                          "gemm or conv3x3 or temporal_conv"], env=env, capture_output=True, text=True, timeout=600)
+                          "(gemm or conv3x3 or temporal_conv) and not subprocess"], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
 
