@@ -254,7 +254,7 @@ int v3d_peer_epoch_bump(void* epoch, void* stream);
  * done_counter: one zeroed u32 of local scratch per stream. */
 int v3d_peer_put(int32_t nseg, const void* const* src, void* const* dst, const int64_t* bytes, int32_t nflag,
                  void* const* flags, const void* epoch, void* done_counter, void* stream);
-/* block the stream until every flag word >= *epoch (bounded: after 5 s the site id is recorded in *status and every later wait
+/* block the stream until every flag word >= *epoch (bounded: after 30 s the site id is recorded in *status and every later wait
  * of the transport returns at once) */
 int v3d_peer_wait(int32_t nflag, const void* const* flags, const void* epoch, void* status, int32_t site,
                   void* stream);

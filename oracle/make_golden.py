@@ -313,7 +313,7 @@ def main(argv):
     if want("encoder_full"):
         _encoder_case(ns, "encoder_full", 128, B=1, hw=128, wseed=8, manifest=manifest)
     if want("clip_small"):
-        _clip_case("clip_small", ref_clip.ClipSpec(image_size=56, patch=14, width=160, layers=2, heads=2, mlp=640,
+        _clip_case("clip_small", ref_clip.ClipSpec(image_size=56, patch=14, width=320, layers=2, heads=4, mlp=1280,
                                                    embed_dim=64), B=2, img_hw=96, wseed=21, manifest=manifest)
     if want("clip_vit_h14"):
         _clip_case("clip_vit_h14", ref_clip.ClipSpec(), B=1, img_hw=512, wseed=22, manifest=manifest)

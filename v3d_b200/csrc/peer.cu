@@ -15,7 +15,7 @@
 //                        (every rank gets bit-identical sums), times `scale`.
 //
 // The epoch is a device word that a one-thread kernel increments at the start of every sharded forward pass, so a
-// captured graph replays with fresh flag values.  Waits are bounded (5 s, and only the first one of a failed transport): a rank that never gets its signal
+// captured graph replays with fresh flag values.  Waits are bounded (30 s - ranks can be seconds apart at their first exchange - and only the first wait of a failed transport pays it): a rank that never gets its signal
 // records the site in a status word and carries on instead of hanging the device; the host checks the status word.
 #include <cstring>
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long kWaitLimitNs = 5ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kWaitLimitNs = 30ull * 1000ull * 1000ull * 1000ull;
 // once one wait of a transport has timed out, every later wait falls through at once (the image is invalid anyway):
 // a broken exchange costs one time limit, not one per site
 __device__ __forceinline__ bool peer_failed(const unsigned int* status) {
