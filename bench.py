@@ -414,7 +414,14 @@ def assemble_line(args, *, world, secs, secs_e2e, launches, clocks, h2d_bytes, d
             "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / temporal conv / implicit 3x3 conv)",
             "achieved": achieved, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved is not None else None,
-            "traffic": traffic, "peak_source": f"{peak_src} bf16_tflops_sustained",
+            # DRAM bytes (read + write) of ONE launch of the dominant kernel at its top-level shape - the implicit 3x3
+            # conv 36 x 64 x 64, 320 -> 320 (algorithmic: A 94.4 MB + W 1.8 MB + D 94.4 MB = 190.6 MB; part of D is
+            # still dirty in L2 at kernel end) - from the round's ncu capture; the other captured kernels in _detail
+            "traffic": (traffic["kernels"].get("gemm_tc_kernel<160, 1, 0, 1> #1", {}).get("traffic")
+                        if traffic else None),
+            "traffic_algorithmic_bytes": 190591488 if traffic else None,
+            "traffic_detail": traffic,
+            "peak_source": f"{peak_src} bf16_tflops_sustained",
             "launches_per_step": len(gemm_records), "algorithmic_tflop_per_step": gemm_flops / 1e12,
             "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
             "breakdown_ms_per_step": breakdown,
