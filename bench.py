@@ -536,7 +536,7 @@ def probe_exchanges(plan):
                         (plan.cfg, "")):
         if obj is None:
             continue
-        for meth, kind in (("allreduce_stats_", "gn_allreduce"), ("exchange_halos", "halo"), ("gather_rows", "kv_allgather"),
+        for meth, kind in (("allreduce_stats_", "gn_allreduce"), ("exchange_halos", "halo"), ("gather_rows", "kv_allgather"), ("gather_signal", "kv_allgather_signal"),
                            ("gather_frames", "frame_gather"), ("gather_halves", "cfg_gather")):
             if hasattr(obj, meth):
                 targets.append((obj, meth, prefix + kind))
