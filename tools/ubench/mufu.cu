@@ -1,6 +1,8 @@
 // Throughput of the exp2 forms a softmax can use, per SM: ex2.approx.ftz.f32 (1 result / lane-op),
 // ex2.approx.f16x2 and ex2.approx.ftz.bf16x2 (2 results / lane-op), plus the conversions around them.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/mufu tools/ubench/mufu.cu && tools/ubench/mufu
+// Finding without running it (cuobjdump -sass): the packed forms compile to TWO MUFU ops on sm_100a
+// (MUFU.EX2.F16 Rd, Ra.H1 and MUFU.EX2.F16 Rd', Ra), so they do not raise the exponential rate of a softmax.
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -269,6 +269,7 @@ class VideoDecoder(KernelModule):
             raise NotImplementedError("skip_video decode is not implemented")
         if not z.is_cuda:
             raise RuntimeError("v3d_b200.VideoDecoder.forward needs CUDA tensors; there is no CPU fallback")
+        ops.require_current_device(z, "v3d_b200.VideoDecoder.forward")
         B, zc, H, W = z.shape
         T = int(timesteps) if timesteps else B
         assert B % T == 0 and zc == self.z_channels

@@ -32,6 +32,15 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
 
 
+def require_current_device(t: torch.Tensor, who: str) -> None:
+    """The library launches on the CURRENT device's current stream and caches per-device kernel attributes per process
+    (one process per GPU is the deployment model): a tensor on another device would be launched on the wrong stream.
+    Called once per forward by the modules."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{who}: tensor on cuda:{t.device.index} but the current device is cuda:"
+                           f"{torch.cuda.current_device()}; call torch.cuda.set_device(...) first (one process per GPU)")
+
+
 def launch_count() -> int:
     return int(_lib.load().v3d_launch_count())
 

@@ -664,6 +664,7 @@ class VideoUNet(KernelModule):
     ) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("v3d_b200.VideoUNet.forward needs CUDA tensors; there is no CPU fallback")
+        ops.require_current_device(x, "v3d_b200.VideoUNet.forward")
         args, dims, graphs = self._prepare(x, timesteps, context, y, time_context, num_video_frames,
                                            image_only_indicator)
         P = self.packed()
