@@ -388,3 +388,42 @@ def test_schedule_cost_accounting_matches_known_flop_budget():
     assert cfg["comm_per_unet_forward"]["cfg_gather"] == [1, 18 * 4 * 64 * 64 * 4]
     views = sc.run(18, 64, "views", 2, 1, 25)
     assert views["comm_per_unet_forward"]["halo"][0] == 44 and views["comm_per_unet_forward"]["kv_allgather"][0] == 16
+
+
+def test_reference_arm_budgets_real_shape_samples(monkeypatch, capsys):
+    """bench.py --impl reference: the CPU-time budget decides how many of the K steps take a real-shape sample (network
+    evaluation of one CFG video at latent 64^2 + decode of nd whole frames); the other steps repeat the calibration
+    forward; the value comes from the real-shape samples only and the line keeps the contract keys and the native
+    arm's `config`.  (Timings stubbed: 1.3 s calibration forward, 30 s per video, 6.5 s per decoded frame.)"""
+    import argparse
+    import json
+
+    import bench
+    import oracle.ref_decoder as rd
+    import oracle.ref_unet as ru
+
+    monkeypatch.setattr(ru, "unet_param_shapes", lambda spec: {"a.weight": (2, 2)})
+    monkeypatch.setattr(rd, "decoder_param_shapes", lambda spec: {"b.weight": (2, 2)})
+    monkeypatch.setattr(bench.CpuReference, "_calibrate_threads", lambda self: (16, {16: 1.3}))
+    monkeypatch.setattr(bench.CpuReference, "_unet", lambda self, L, videos=2: 1.3 if L == 8 else 30.0 * videos)
+    monkeypatch.setattr(bench.CpuReference, "_dec", lambda self, L, frames=0: 6.5 * (frames or self.T))
+    monkeypatch.setattr(bench.CpuReference, "BUDGET_S", 420.0)
+    args = argparse.Namespace(frames=18, edm_steps=25, latent=64, steps=20, warmup=5, gpus=1, min_cfg=3.5, max_cfg=3.5,
+                              shard="images")
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    cb = line["cpu_baseline"]
+    assert line["impl"] == "reference" and cb["mode"] == "real-shape" and cb["kind"] == "port"
+    assert cb["real_shape_samples"] == 5 and len(cb["calibration_forward_drift_s"]) == 15
+    assert cb["per_sample_unet_forward_s"] == [60.0] * 5 and cb["per_sample_decode_s"] == [117.0] * 5
+    assert line["value"] == pytest.approx(18 / (25 * 60.0 + 117.0)) and line["e2e"]["value"] == line["value"]
+    assert line["config"] == bench.workload_config(args, "gpu")          # the same dictionary in both arms
+    # the in-line cpu_baseline of the native arm: one bounded sample
+    monkeypatch.setattr(bench.CpuReference, "BUDGET_S", 45.0)
+    ref = bench.CpuReference(18, 25, 64, n_samples=1)
+    tu, td = ref.sample()
+    assert ref.mode == "real-shape" and ref.n_real == 1 and ref.nd == 2 and (tu, td) == (60.0, 6.5 * 2 * 9)
+    # a budget too small for even one real-shape sample: the affine ladder, and the line says so
+    monkeypatch.setattr(bench.CpuReference, "BUDGET_S", 20.0)
+    ref = bench.CpuReference(18, 25, 64, n_samples=3)
+    assert ref.mode == "ladder" and "did not allow the real shape" in ref.describe()
