@@ -1,21 +1,28 @@
 #!/usr/bin/env bash
-# First GPU session of a round: what to run, in which order, with what time bound.  Every stage writes its log under
-# gpurun_out/ (merged back by gpurun) and is wrapped in `timeout`, so a hang in not-yet-validated code costs minutes,
-# not the box.  Usage (from the repo root, one stage list per gpurun call):
-#     gpurun --timeout 1500 -- 'bash tools/gpu_round.sh tests firstrun pair'
-#     gpurun --timeout 1200 -- 'bash tools/gpu_round.sh bench ncu_launches'
+# A GPU session, stage by stage: what to run, in which order, with what time bound.  Every stage writes its log under
+# gpurun_out/ (merged back by gpurun: keep it below 64 MiB - one `--set full --import-source on` report of 40 launches is
+# already 47 MB; move old reports away first) and is wrapped in `timeout`, so a hang costs minutes, not the box.
+# Usage (from the repo root, one stage list per gpurun call):
+#     gpurun --timeout 1500 -- 'bash tools/gpu_round.sh tests bench'
+#     gpurun --timeout 900  -- 'bash tools/gpu_round.sh ncu_set ncu_launches'
 #     gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_round.sh viewshard2'
+#     gpurun --gpus 4 --timeout 900  -- 'NGPU=4 bash tools/gpu_round.sh nccl_tests strongN'
 # Stages:
 #   tests         the GPU suite (pytest -m gpu)
-#   pair          cta_group::2 GEMM tiles (V3D_GEMM_2CTA=1) under a 300 s timeout, then the per-shape microbenchmark
-#                 with the switch off / on
-#   rtma          TMA-staged residual epilogue (V3D_GEMM_RTMA=1): tests, then per-shape timings
+#   pair / rtma   the GEMM / conv tests with the CTA-pair (V3D_GEMM_2CTA=1) or TMA-staged-residual (V3D_GEMM_RTMA=1) tiles
+#                 forced on, then the per-shape microbenchmark with the switch off / on
 #   attn_poly     FMA-pipe exp2 variants of the spatial attention (V3D_ATTN_POLY=1..3): tests, then timings 0..3
-#   bench         bench.py (default N=1) -> gpurun_out/bench.json ; bench.py --impl reference -> bench_ref.json
+#   micro_all     tools/microbench.py: every kernel family at its V3D_512 shapes
+#   bench         bench.py (default N=1) -> gpurun_out/bench.json
+#   bench_ref     bench.py --impl reference (host cores only, but the box time is charged all the same)
 #   sweep         BASELINE configs[4]: S in {10,25,50} x T in {14,18,25} on one GPU -> gpurun_out/sweep.json
 #   ncu_launches  the ncu launch list of one EDM step + decode (gpu__time_duration.sum, --clock-control none)
-#   ncu_full      ncu --set full of the named kernels (GEMM conv/geglu/proj, attention, GroupNorm, LayerNorm)
-#   viewshard2    (2 GPUs) NCCL engine parity test, then bench.py --shard views and --shard images at N=2
+#   ncu_set       ONE ncu --set full run over every kernel family at its top-level shape (tools/microbench.py ncu_set)
+#   ncu_full      ncu --set full of the named kernels inside bench.py (GEMM, attention, GroupNorm, LayerNorm)
+#   viewshard2    (2 GPUs) the one-image-over-ranks parity tests, then the default line (image-parallel + `strong`) and
+#                 the frame-sharded plan over torch.distributed collectives for comparison
+#   nccl_tests    (NGPU GPUs) only the tests that need several GPUs
+#   strongN       (NGPU GPUs) the default line: image-parallel value + `strong` (one image over the NGPU GPUs)
 set -u
 mkdir -p gpurun_out
 PY=python
@@ -81,6 +88,8 @@ for stage in "$@"; do
         --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --shard views --steps 2 --warmup 3 --no-parity
       V3D_SHARD_TRANSPORT=nccl V3D_VIEWSHARD_GRAPH=1 run 900 bench_views2_nccl_graph.json $PY -m torch.distributed.run --nnodes=1 \
         --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --shard views --steps 2 --warmup 3 --no-parity ;;
+    nccl_tests)
+      run 700 viewshard_nccl_tests.log $PY -m pytest tests/test_viewshard_gpu.py -m gpu -q -s -x -k "nccl or cfg_views_engine_peer_transport" ;;
     strongN)
       # (N GPUs, N = $NGPU) the default line (image-parallel + `strong` sub-object)
       run 900 bench_n${NGPU:-8}.json $PY -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 \
