@@ -24,10 +24,10 @@ ROOT = str(Path(__file__).resolve().parent.parent)
 DEV = "cuda"
 
 # The gloo-staged variants (exchanges copied through host memory, all ranks on cuda:0) spawn 2-4 model-building
-# processes each and add ~2.5 minutes to the GPU suite.  They exercise no device code that the peer-transport variants
-# below do not (same kernels, same schedules) and their host logic is proven bit-exact over gloo in the CPU suite
-# (tests/test_host_schedule_cpu.py), so they run on request only; the default suite keeps the peer-transport variants on
-# one GPU and every NCCL variant when the box has the GPUs.
+# processes each.  The frame-block plan stays in the default suite (it covers the torch.distributed fallback transport on
+# a one-GPU box); the CFG-pair and the 4-process composite duplicates exercise no device code that the peer-transport
+# variants below do not (same kernels, same schedules), their host logic is proven bit-exact over gloo in the CPU suite
+# (tests/test_host_schedule_cpu.py) and they add ~2 minutes, so they run on request only.
 slow = pytest.mark.skipif(os.environ.get("V3D_SLOW_TESTS") != "1", reason="gloo-staged duplicate of the peer-transport "
                           "test (set V3D_SLOW_TESTS=1)")
 
@@ -230,7 +230,6 @@ def _run_engine_pair(backend: str, one_gpu: bool, T: int = 5, world: int = 2, tr
         assert r["exchanges"]["kv_allgather"] > 0 and r["exchanges"]["halo"] >= r["exchanges"]["gn_allreduce"] > 0
 
 
-@slow
 def test_view_sharded_engine_matches_unsharded_one_gpu_gloo():
     _run_engine_pair("gloo", one_gpu=True)
 
