@@ -402,6 +402,8 @@ def test_reference_arm_budgets_real_shape_samples(monkeypatch, capsys):
     import oracle.ref_decoder as rd
     import oracle.ref_unet as ru
 
+    monkeypatch.setattr(torch, "set_num_threads", lambda n: None)   # the arm pins its calibrated thread count: keep this
+                                                                   # session's (bit-exact tests downstream depend on it)
     monkeypatch.setattr(ru, "unet_param_shapes", lambda spec: {"a.weight": (2, 2)})
     monkeypatch.setattr(rd, "decoder_param_shapes", lambda spec: {"b.weight": (2, 2)})
     monkeypatch.setattr(bench.CpuReference, "_calibrate_threads", lambda self: (16, {16: 1.3}))
